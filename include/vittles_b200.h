@@ -1,0 +1,141 @@
+/* vittles_b200 - C ABI of the B200-native sensitivity hot path.
+ *
+ * The reference (rgiordan/vittles) is pure Python: it has no FFI or plugin
+ * registry.  Its seam is the solver-closure protocol `solve(v) -> H^{-1} v`
+ * (vittles/solver_lib.py:22-30) plus the constructors exported from
+ * vittles/__init__.py:1-8.  This header is the boundary a maintainer would
+ * bind (ctypes stub in INTEGRATION.md) to move the arithmetic behind those
+ * Python entry points onto a B200.  Each function cites the reference code it
+ * replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to float64 unless stated otherwise;
+ *     matrices are row-major with an explicit leading dimension (elements);
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous with
+ *     respect to the host unless stated otherwise;
+ *   - the return value is 0 on success or a VT_ERR_* code; the message of the
+ *     last failure on the calling thread is returned by vt_last_error();
+ *   - the library holds no global state and never allocates device memory:
+ *     workspaces are sized by the *_workspace_bytes queries and owned by the
+ *     caller.
+ */
+#ifndef VITTLES_B200_H
+#define VITTLES_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VT_OK 0
+#define VT_ERR_CUDA 1            /* CUDA runtime / launch failure            */
+#define VT_ERR_INVALID 2         /* bad argument -> ValueError upstream      */
+#define VT_ERR_NOT_PD 3          /* non-positive pivot -> LinAlgError        */
+#define VT_ERR_NO_CONVERGENCE 4  /* CG hit maxiter -> UserWarning upstream   */
+
+#define VT_GLM_LOGISTIC 0
+#define VT_GLM_POISSON 1
+#define VT_GLM_GAUSSIAN 2
+
+#define VT_OP_KC 0 /* operand element (r,k) at p[r*ld + k]  (k contiguous) */
+#define VT_OP_KS 1 /* operand element (r,k) at p[k*ld + r]  (k strided)    */
+
+const char* vt_last_error(void);
+int vt_abi_version(void);
+/* Number of kernels this library has launched in the process so far. */
+int64_t vt_launch_count(void);
+/* SM count and compute capability of the current device. */
+int vt_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Runs a register-resident DMMA loop for about `seconds` and returns the
+ * achieved FP64 tensor TFLOP/s: the roofline denominator bench.py reports
+ * (MEASURED_PEAKS.json has no FP64 entry).  Synchronous. */
+int vt_fp64_peak_probe(double seconds, double* tflops, void* stream);
+
+/* ---- FP64 tensor-core GEMM engine ---------------------------------------
+ * C(m,n) = alpha * rowscale[m] * colscale[n] * sum_k kscale[k] A(m,k) B(n,k) + beta * C(m,n)
+ * (scale vectors may be NULL; kscale requires both operands in VT_OP_KS).
+ * lower != 0: only the lower triangle of a square C is produced; mirror != 0
+ * additionally writes the transposed entries (exactly symmetric result).
+ * Replaces the numpy `@` / einsum GEMMs at sensitivity_lib.py:67,76,247 and
+ * lr_cov_lib.py:172 and is the engine under every routine below.            */
+size_t vt_dgemm_workspace_bytes(int M, int N, int K, int lower);
+int vt_dgemm(int M, int N, int K, double alpha, const double* A, int64_t lda, int amode, const double* B,
+             int64_t ldb, int bmode, double beta, double* C, int64_t ldc, const double* kscale,
+             const double* colscale, const double* rowscale, int lower, int mirror, void* workspace,
+             size_t workspace_bytes, void* stream);
+
+/* ---- Hessian assembly ----------------------------------------------------
+ * H = X^T diag(s) X + l2 * I for X (N x D).  Replaces
+ * autograd.hessian(objective)(theta, w) for GLM objectives
+ * (sensitivity_lib.py:381-383, lr_cov_lib.py:102).  Deterministic split-K.   */
+size_t vt_syrk_workspace_bytes(int64_t N, int D);
+int vt_syrk_weighted(const double* X, int64_t ldx, int64_t N, int D, const double* s, double l2, double* H,
+                     int64_t ldh, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- GLM passes over X (HBM bound, one read of X each) --------------------
+ * vt_glm_stats: z = X theta, resid = b'(z) - y, s = w b''(z),
+ *               grad = X^T (w resid) + l2 theta   (sensitivity_lib.py:354 grad;
+ *               the optimum check at :203-215).  Outputs may be NULL.
+ * vt_glm_hvp:   out = X^T (s .* (X v)) + ridge v  - the mat_times_vec handed
+ *               to get_cg_solver (solver_lib.py:76-79,91).
+ * vt_glm_dirderiv: out = X^T (w .* b^{(q+1)}(z) .* prod_j X dirs_j), the
+ *               closed form of the nested JVPs of
+ *               ForwardModeDerivativeArray.eval_directional_derivative
+ *               (sensitivity_lib.py:788-807) for q eta-directions.           */
+size_t vt_glm_workspace_bytes(int D);
+int vt_glm_stats(const double* X, int64_t ldx, int64_t N, int D, const double* theta, const double* y,
+                 const double* w, int family, double* z, double* resid, double* s, double* grad, double l2,
+                 void* workspace, size_t workspace_bytes, void* stream);
+int vt_glm_hvp(const double* X, int64_t ldx, int64_t N, int D, const double* s, const double* v, double ridge,
+               double* out, void* workspace, size_t workspace_bytes, void* stream);
+int vt_glm_dirderiv(const double* X, int64_t ldx, int64_t N, int D, const double* z, const double* w, int family,
+                    const double* dirs, int q, double* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- Dense Cholesky solver -------------------------------------------------
+ * vt_potrf / vt_potrs replace scipy.linalg.cho_factor / cho_solve behind
+ * get_dense_cholesky_solver (solver_lib.py:27,29).  A is overwritten by its
+ * lower factor; `dinv` (vt_potrf_dinv_doubles(D) doubles) receives the inverted
+ * 128x128 diagonal blocks used by the solve; *info (device int32) is 0 or the
+ * 1-based column of the first non-positive pivot (LinAlgError upstream).
+ * vt_potrs solves in place for a row-major D x K right-hand side.            */
+size_t vt_potrf_dinv_doubles(int D);
+int vt_potrf(double* A, int64_t lda, int D, double* dinv, int32_t* info, void* stream);
+int vt_potrs(const double* L, int64_t ldl, int D, const double* dinv, double* B, int64_t ldb, int K, void* stream);
+
+/* ---- Infinitesimal-jackknife apply ----------------------------------------
+ * S (D x N) = -Hinv (D x D) * G^T, column n of G^T being resid[n] * x_n, fused
+ * so that the cross-Hessian G^T is never materialised.  Replaces
+ * `_sens_mat = -hess_solver(cross_hess)` (sensitivity_lib.py:226) for
+ * lambda := per-observation weights.                                        */
+int vt_ij_apply(const double* Hinv, int64_t ldh, const double* X, int64_t ldx, int64_t N, int D,
+                const double* resid, double* S, int64_t lds, void* stream);
+
+/* ---- Prediction GEMV --------------------------------------------------------
+ * y = alpha * A x + beta * y0 for row-major A (M x N), N long:
+ * theta_hat + S (lam1 - lam0)   (sensitivity_lib.py:245-247).                */
+size_t vt_gemv_workspace_bytes(int M, int64_t N);
+int vt_gemv(const double* A, int64_t lda, int M, int64_t N, const double* x, double alpha, const double* y0,
+            double beta, double* y, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- Conjugate-gradient vector kernels --------------------------------------
+ * One scipy-cg iteration (solver_lib.py:93) is
+ *   vt_cg_update_p  ->  q = mat_times_vec(p)  ->  vt_cg_update_xr.
+ * `state` is 8 device doubles: {rho, rho_prev, p.q, |r|^2, |b|^2, ...}.      */
+int vt_cg_init(int D, const double* b, double* x, double* r, double* state, void* stream);
+int vt_cg_update_p(int D, const double* r, double* p, double* state, int first, void* stream);
+int vt_cg_update_xr(int D, const double* p, const double* q, double* x, double* r, double* state, void* stream);
+
+/* ---- Synthetic data (bench and tests) ---------------------------------------
+ * Counter-based, reproducible for any row range (oracle twin:
+ * oracle/models.py synth_design / synth_uniform).                            */
+int vt_synth_design(double* X, int64_t ldx, int64_t row0, int64_t nrows, int ncols, uint64_t seed, double scale,
+                    void* stream);
+int vt_synth_uniform(double* u, int64_t row0, int64_t nrows, uint64_t seed, void* stream);
+int vt_synth_bernoulli(double* y, const double* z, int64_t row0, int64_t nrows, uint64_t seed, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITTLES_B200_H */

@@ -56,7 +56,8 @@ class QuadraticModel:
         def f(theta_flat, lam_flat):
             theta = self._fold_t(theta_flat, theta_free)
             lam = self._fold_t(lam_flat, lambda_free)
-            return 0.5 * theta @ self._A @ theta + lam @ theta
+            A = self._A.to(theta.device)
+            return 0.5 * theta @ A @ theta + lam @ theta
         return f
 
     def get_flat_hyper_par_objective(self, theta_free, lambda_free):
@@ -68,7 +69,7 @@ class QuadraticModel:
         """torch map lam_flat -> theta_flat (closed form), differentiable."""
         def opt(lam_flat):
             lam = self._fold_t(lam_flat, lambda_free)
-            theta = -1 * torch.linalg.solve(self._A, lam)
+            theta = -1 * torch.linalg.solve(self._A.to(lam.device), lam)
             return self._flatten_t(theta, theta_free)
         return opt
 

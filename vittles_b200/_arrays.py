@@ -1,0 +1,41 @@
+"""Array plumbing: the reference works on numpy arrays; this build computes on
+float64 CUDA tensors.  Inputs may be numpy arrays, python sequences or torch
+tensors on any device; results are returned in the kind of the input they
+correspond to (numpy in -> numpy out), so existing numpy code keeps working,
+while CUDA tensors stay on the device end to end."""
+import numpy as np
+import torch
+
+
+def default_device():
+    if not torch.cuda.is_available():
+        raise RuntimeError('vittles_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def to_device(a, device=None):
+    """float64 CUDA tensor from numpy / sequence / tensor (no copy if already there)."""
+    if device is None:
+        device = default_device()
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device, dtype=torch.float64)
+    return torch.as_tensor(np.asarray(a, dtype=np.float64), device=device)
+
+
+def kind_of(a):
+    """'numpy', 'cpu' or 'cuda' - how a result matching `a` should be returned."""
+    if isinstance(a, torch.Tensor):
+        return 'cuda' if a.is_cuda else 'cpu'
+    return 'numpy'
+
+
+def as_kind(t, kind):
+    if kind == 'cuda':
+        return t
+    if kind == 'cpu':
+        return t.cpu()
+    return t.detach().cpu().numpy()
+
+
+def like(t, proto):
+    return as_kind(t, kind_of(proto))

@@ -1,0 +1,211 @@
+// extern "C" entry points declared in include/vittles_b200.h.
+#include "../../include/vittles_b200.h"
+#include "chol.cuh"
+#include "common.cuh"
+#include "dgemm.cuh"
+#include "glm.cuh"
+#include "synth.cuh"
+
+namespace vt {
+const char* last_error();
+
+namespace {
+__global__ void add_diag_kernel(double* H, long ldh, int D, double v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < D) H[(long)i * ldh + i] += v;
+}
+
+// Register-resident DMMA loop (same kernel as tools/fp64_peak.cu, variant
+// dmma884_t16): 16 independent accumulator tiles per warp, 2 warps per SMSP.
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, double a, double b, int iters) {
+  double c[16][2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { c[i][0] = threadIdx.x; c[i][1] = i; }
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dmma884(c[i][0], c[i][1], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += c[i][0] + c[i][1];
+  if (s == 12345.678) out[0] = s;
+}
+}  // namespace
+}  // namespace vt
+
+using namespace vt;
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+const char* vt_last_error(void) { return vt::last_error(); }
+int vt_abi_version(void) { return 1; }
+int64_t vt_launch_count(void) { return (int64_t)vt::launch_count(); }
+
+int vt_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  VT_CUDA(cudaGetDevice(&dev));
+  if (sm_count) VT_CUDA(cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, dev));
+  if (cc_major) VT_CUDA(cudaDeviceGetAttribute(cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (cc_minor) VT_CUDA(cudaDeviceGetAttribute(cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+  return VT_OK;
+}
+
+int vt_fp64_peak_probe(double seconds, double* tflops, void* stream) {
+  VT_REQUIRE(tflops && seconds > 0, "fp64_peak_probe: bad arguments");
+  double* out = nullptr;
+  VT_CUDA(cudaMalloc(&out, 8));   // the one allocation in the library: 8 bytes, freed below
+  cudaEvent_t e0, e1;
+  VT_CUDA(cudaEventCreate(&e0));
+  VT_CUDA(cudaEventCreate(&e1));
+  const int grid = num_sms(), iters0 = 1 << 14;
+  auto run = [&](int iters, float* ms) -> int {
+    VT_CUDA(cudaEventRecord(e0, S(stream)));
+    dmma_peak_kernel<<<grid, 256, 0, S(stream)>>>(out, 1.0000001, 1e-9, iters);
+    VT_LAUNCH_CHECK();
+    VT_CUDA(cudaEventRecord(e1, S(stream)));
+    VT_CUDA(cudaEventSynchronize(e1));
+    VT_CUDA(cudaEventElapsedTime(ms, e0, e1));
+    return VT_OK;
+  };
+  float ms = 0.f;
+  int st = run(iters0, &ms);          // warm-up + calibration
+  if (st == VT_OK) st = run(iters0, &ms);
+  if (st == VT_OK) {
+    double want = seconds * 1e3 / (ms > 1e-3f ? ms : 1e-3f) * iters0;
+    int iters = want > 2e9 ? 2000000000 : (int)want;
+    if (iters < iters0) iters = iters0;
+    st = run(iters, &ms);
+    if (st == VT_OK) *tflops = 512.0 * 16.0 * 8.0 * (double)grid * (double)iters / (ms * 1e-3) / 1e12;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  return st;
+}
+
+size_t vt_dgemm_workspace_bytes(int M, int N, int K, int lower) { return gemm_workspace_bytes(M, N, K, lower); }
+
+int vt_dgemm(int M, int N, int K, double alpha, const double* A, int64_t lda, int amode, const double* B,
+             int64_t ldb, int bmode, double beta, double* C, int64_t ldc, const double* kscale,
+             const double* colscale, const double* rowscale, int lower, int mirror, void* workspace,
+             size_t workspace_bytes, void* stream) {
+  VT_REQUIRE((amode == KC || amode == KS) && (bmode == KC || bmode == KS), "dgemm: bad operand mode");
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.A = A; p.lda = lda; p.amode = amode;
+  p.B = B; p.ldb = ldb; p.bmode = bmode;
+  p.C = C; p.ldc = ldc;
+  p.alpha = alpha; p.beta = beta;
+  p.kscale = kscale; p.colscale = colscale; p.rowscale = rowscale;
+  p.lower = lower; p.mirror = mirror;
+  p.parts = 0;
+  p.workspace = static_cast<double*>(workspace);
+  p.workspace_bytes = workspace_bytes;
+  return gemm_launch(p, S(stream));
+}
+
+size_t vt_syrk_workspace_bytes(int64_t N, int D) {
+  return gemm_workspace_bytes(D, D, (int)(N > 2147483647LL ? 2147483647LL : N), 1);
+}
+
+int vt_syrk_weighted(const double* X, int64_t ldx, int64_t N, int D, const double* s, double l2, double* H,
+                     int64_t ldh, void* workspace, size_t workspace_bytes, void* stream) {
+  VT_REQUIRE(X && H, "syrk_weighted: null pointer");
+  VT_REQUIRE(N >= 1 && N <= 2147483647LL && D >= 1 && ldx >= D && ldh >= D, "syrk_weighted: bad shape");
+  GemmParams p{};
+  p.M = D; p.N = D; p.K = (int)N;
+  p.A = X; p.lda = ldx; p.amode = KS;
+  p.B = X; p.ldb = ldx; p.bmode = KS;
+  p.C = H; p.ldc = ldh;
+  p.alpha = 1.0; p.beta = 0.0;
+  p.kscale = s;
+  p.lower = 1; p.mirror = 1;
+  p.parts = 0;
+  p.workspace = static_cast<double*>(workspace);
+  p.workspace_bytes = workspace_bytes;
+  int st = gemm_launch(p, S(stream));
+  if (st != VT_OK) return st;
+  if (l2 != 0.0) {
+    add_diag_kernel<<<(D + 255) / 256, 256, 0, S(stream)>>>(H, ldh, D, l2);
+    VT_LAUNCH_CHECK();
+  }
+  return VT_OK;
+}
+
+size_t vt_glm_workspace_bytes(int D) { return glm_workspace_bytes(D); }
+
+int vt_glm_stats(const double* X, int64_t ldx, int64_t N, int D, const double* theta, const double* y,
+                 const double* w, int family, double* z, double* resid, double* s, double* grad, double l2,
+                 void* workspace, size_t workspace_bytes, void* stream) {
+  return glm_stats(X, ldx, N, D, theta, y, w, family, z, resid, s, grad, l2, static_cast<double*>(workspace),
+                   workspace_bytes, S(stream));
+}
+
+int vt_glm_hvp(const double* X, int64_t ldx, int64_t N, int D, const double* s, const double* v, double ridge,
+               double* out, void* workspace, size_t workspace_bytes, void* stream) {
+  return glm_hvp(X, ldx, N, D, s, v, ridge, out, static_cast<double*>(workspace), workspace_bytes, S(stream));
+}
+
+int vt_glm_dirderiv(const double* X, int64_t ldx, int64_t N, int D, const double* z, const double* w, int family,
+                    const double* dirs, int q, double* out, void* workspace, size_t workspace_bytes, void* stream) {
+  return glm_dirderiv(X, ldx, N, D, z, w, family, dirs, q, out, static_cast<double*>(workspace), workspace_bytes,
+                      S(stream));
+}
+
+size_t vt_potrf_dinv_doubles(int D) { return chol_dinv_doubles(D); }
+
+int vt_potrf(double* A, int64_t lda, int D, double* dinv, int32_t* info, void* stream) {
+  return chol_potrf(A, lda, D, dinv, info, S(stream));
+}
+
+int vt_potrs(const double* L, int64_t ldl, int D, const double* dinv, double* B, int64_t ldb, int K, void* stream) {
+  return chol_potrs(L, ldl, D, dinv, B, ldb, K, S(stream));
+}
+
+int vt_ij_apply(const double* Hinv, int64_t ldh, const double* X, int64_t ldx, int64_t N, int D,
+                const double* resid, double* Sout, int64_t lds, void* stream) {
+  VT_REQUIRE(Hinv && X && resid && Sout, "ij_apply: null pointer");
+  VT_REQUIRE(N >= 1 && N <= 2147483647LL && D >= 1 && ldh >= D && ldx >= D && lds >= N, "ij_apply: bad shape");
+  GemmParams p{};
+  p.M = D; p.N = (int)N; p.K = D;
+  p.A = Hinv; p.lda = ldh; p.amode = KC;
+  p.B = X; p.ldb = ldx; p.bmode = KC;
+  p.C = Sout; p.ldc = lds;
+  p.alpha = -1.0; p.beta = 0.0;
+  p.colscale = resid;
+  p.parts = 1;
+  return gemm_launch(p, S(stream));
+}
+
+size_t vt_gemv_workspace_bytes(int M, int64_t N) { return gemv_workspace_bytes(M, N); }
+
+int vt_gemv(const double* A, int64_t lda, int M, int64_t N, const double* x, double alpha, const double* y0,
+            double beta, double* y, void* workspace, size_t workspace_bytes, void* stream) {
+  return gemv_rows(A, lda, M, N, x, alpha, y0, beta, y, static_cast<double*>(workspace), workspace_bytes, S(stream));
+}
+
+int vt_cg_init(int D, const double* b, double* x, double* r, double* state, void* stream) {
+  return cg_init(D, b, x, r, state, S(stream));
+}
+int vt_cg_update_p(int D, const double* r, double* p, double* state, int first, void* stream) {
+  return cg_update_p(D, r, p, state, first, S(stream));
+}
+int vt_cg_update_xr(int D, const double* p, const double* q, double* x, double* r, double* state, void* stream) {
+  return cg_update_xr(D, p, q, x, r, state, S(stream));
+}
+
+int vt_synth_design(double* X, int64_t ldx, int64_t row0, int64_t nrows, int ncols, uint64_t seed, double scale,
+                    void* stream) {
+  return synth_design(X, ldx, row0, nrows, ncols, seed, scale, S(stream));
+}
+int vt_synth_uniform(double* u, int64_t row0, int64_t nrows, uint64_t seed, void* stream) {
+  return synth_uniform(u, row0, nrows, seed, S(stream));
+}
+int vt_synth_bernoulli(double* y, const double* z, int64_t row0, int64_t nrows, uint64_t seed, void* stream) {
+  return synth_bernoulli(y, z, row0, nrows, seed, S(stream));
+}
+
+}  // extern "C"

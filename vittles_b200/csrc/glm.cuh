@@ -1,0 +1,36 @@
+// Host-side launchers of the GLM-family kernels (glm.cu).
+#pragma once
+#include "common.cuh"
+
+namespace vt {
+
+enum GlmFamily : int { GLM_LOGISTIC = 0, GLM_POISSON = 1, GLM_GAUSSIAN = 2 };
+constexpr int GLM_MAX_BDERIV = 8;   // highest derivative order of b(z) supported
+
+size_t glm_workspace_bytes(int D);
+
+// z = X theta; resid = b'(z) - y; s = w b''(z); grad = X^T (w resid) + l2 theta.
+// Any of z/resid/s/grad may be null.
+int glm_stats(const double* X, long ldx, long N, int D, const double* theta, const double* y, const double* w,
+              int family, double* z, double* resid, double* s, double* grad, double l2, double* workspace,
+              size_t workspace_bytes, cudaStream_t stream);
+
+// out = X^T (s .* (X v)) + ridge * v
+int glm_hvp(const double* X, long ldx, long N, int D, const double* s, const double* v, double ridge, double* out,
+            double* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+// out = X^T ( w .* b^{(q+1)}(z) .* prod_j (X dirs_j) ),  dirs is (q, D) row-major
+int glm_dirderiv(const double* X, long ldx, long N, int D, const double* z, const double* w, int family,
+                 const double* dirs, int q, double* out, double* workspace, size_t workspace_bytes,
+                 cudaStream_t stream);
+
+size_t gemv_workspace_bytes(int M, long N);
+// y = alpha * A x + beta * y0, A (M x N) row-major with leading dimension lda
+int gemv_rows(const double* A, long lda, int M, long N, const double* x, double alpha, const double* y0, double beta,
+              double* y, double* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+int cg_init(int D, const double* b, double* x, double* r, double* state, cudaStream_t stream);
+int cg_update_p(int D, const double* r, double* p, double* state, int first, cudaStream_t stream);
+int cg_update_xr(int D, const double* p, const double* q, double* x, double* r, double* state, cudaStream_t stream);
+
+}  // namespace vt

@@ -1,0 +1,287 @@
+"""Tensor-level wrappers over the C ABI.
+
+Each function takes float64 CUDA tensors, sizes the workspace the library asks
+for, launches on the current stream and returns tensors.  No arithmetic on the
+hot path happens in torch: torch is the allocator and the stream provider.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import check, ptr, stream
+
+_workspaces = {}
+
+
+def _ws(key, nbytes, device):
+    """Grow-only per-device scratch buffer, keyed by purpose."""
+    nbytes = int(nbytes)
+    if nbytes == 0:
+        return None, 0
+    k = (key, device.index)
+    buf = _workspaces.get(k)
+    if buf is None or buf.numel() * 8 < nbytes:
+        buf = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=device)
+        _workspaces[k] = buf
+    return buf, buf.numel() * 8
+
+
+def free_workspaces():
+    _workspaces.clear()
+
+
+def _f64(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.float64:
+        raise TypeError('{} must be a float64 CUDA tensor'.format(name))
+    return t
+
+
+def _mat(t, name):
+    _f64(t, name)
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError('{} must be a row-major 2-d tensor (unit stride in the last dimension)'.format(name))
+    return t
+
+
+def _ld(t):
+    # leading dimension of a row-major matrix (handles single-row views)
+    return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
+
+
+def device_info():
+    lib = _cabi.require_cuda()
+    sm, ma, mi = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    check(lib.vt_device_info(ctypes.byref(sm), ctypes.byref(ma), ctypes.byref(mi)))
+    return dict(sm_count=sm.value, cc=(ma.value, mi.value))
+
+
+def launch_count():
+    return int(_cabi.load().vt_launch_count())
+
+
+def fp64_peak_probe(seconds=0.3):
+    lib = _cabi.require_cuda()
+    tf = ctypes.c_double()
+    check(lib.vt_fp64_peak_probe(float(seconds), ctypes.byref(tf), stream()))
+    return tf.value
+
+
+# ------------------------------------------------------------------ GEMM ----
+def gemm(A, B, amode='KC', bmode='KC', alpha=1.0, beta=0.0, out=None, M=None, N=None, K=None,
+         kscale=None, colscale=None, rowscale=None, lower=False, mirror=False):
+    """out(m,n) = alpha * rs[m] cs[n] sum_k ks[k] A(m,k) B(n,k) + beta * out.
+
+    ``KC``: the tensor is (rows, K); ``KS``: the tensor is (K, rows)."""
+    lib = _cabi.require_cuda()
+    _mat(A, 'A'); _mat(B, 'B')
+    am = _cabi.OP_KC if amode == 'KC' else _cabi.OP_KS
+    bm = _cabi.OP_KC if bmode == 'KC' else _cabi.OP_KS
+    m, ka = (A.shape if am == _cabi.OP_KC else A.shape[::-1])
+    n, kb = (B.shape if bm == _cabi.OP_KC else B.shape[::-1])
+    M = m if M is None else M
+    N = n if N is None else N
+    K = ka if K is None else K
+    if ka != kb and K is None:
+        raise ValueError('gemm: inner dimensions differ ({} vs {})'.format(ka, kb))
+    if out is None:
+        if beta != 0.0:
+            raise ValueError('gemm: beta != 0 needs `out`')
+        out = torch.empty((M, N), dtype=torch.float64, device=A.device)
+    _mat(out, 'out')
+    wsb = lib.vt_dgemm_workspace_bytes(M, N, K, int(lower))
+    ws, wsb = _ws('gemm', wsb, A.device)
+    check(lib.vt_dgemm(M, N, K, float(alpha), ptr(A), _ld(A), am, ptr(B), _ld(B), bm, float(beta), ptr(out),
+                       _ld(out), ptr(kscale), ptr(colscale), ptr(rowscale), int(lower), int(mirror), ptr(ws), wsb,
+                       stream()))
+    return out
+
+
+# ------------------------------------------------------- Hessian assembly ----
+def syrk_weighted(X, s=None, l2=0.0, out=None):
+    """H = X^T diag(s) X + l2 I  (FP64 DMMA, deterministic split-K)."""
+    lib = _cabi.require_cuda()
+    _mat(X, 'X')
+    N, D = X.shape
+    if s is None:
+        s = torch.ones(N, dtype=torch.float64, device=X.device)
+    _f64(s, 's')
+    if s.numel() != N:
+        raise ValueError('s must have one entry per row of X')
+    if out is None:
+        out = torch.empty((D, D), dtype=torch.float64, device=X.device)
+    wsb = lib.vt_syrk_workspace_bytes(N, D)
+    ws, wsb = _ws('syrk', wsb, X.device)
+    check(lib.vt_syrk_weighted(ptr(X), _ld(X), N, D, ptr(s), float(l2), ptr(out), _ld(out), ptr(ws), wsb, stream()))
+    return out
+
+
+# ------------------------------------------------------------- GLM passes ----
+def glm_stats(X, theta, y, w=None, family='logistic', l2=0.0, want_grad=True, want_z=True):
+    """One pass over X: z = X theta, resid = b'(z) - y, s = w b''(z) and
+    (optionally) grad = X^T (w resid) + l2 theta."""
+    lib = _cabi.require_cuda()
+    _mat(X, 'X')
+    N, D = X.shape
+    dev = X.device
+    z = torch.empty(N, dtype=torch.float64, device=dev) if want_z else None
+    resid = torch.empty(N, dtype=torch.float64, device=dev)
+    s = torch.empty(N, dtype=torch.float64, device=dev)
+    grad = torch.empty(D, dtype=torch.float64, device=dev) if want_grad else None
+    ws, wsb = _ws('glm', lib.vt_glm_workspace_bytes(D), dev)
+    check(lib.vt_glm_stats(ptr(X), _ld(X), N, D, ptr(_f64(theta, 'theta').contiguous()), ptr(_f64(y, 'y')),
+                           ptr(w), _cabi.GLM_FAMILIES[family], ptr(z), ptr(resid), ptr(s), ptr(grad), float(l2),
+                           ptr(ws), wsb, stream()))
+    return z, resid, s, grad
+
+
+def glm_hvp(X, s, v, ridge=0.0, out=None):
+    """out = X^T (s .* (X v)) + ridge v  - one fused pass over X."""
+    lib = _cabi.require_cuda()
+    _mat(X, 'X')
+    N, D = X.shape
+    if out is None:
+        out = torch.empty(D, dtype=torch.float64, device=X.device)
+    ws, wsb = _ws('glm', lib.vt_glm_workspace_bytes(D), X.device)
+    check(lib.vt_glm_hvp(ptr(X), _ld(X), N, D, ptr(_f64(s, 's')), ptr(_f64(v, 'v').contiguous()), float(ridge),
+                         ptr(out), ptr(ws), wsb, stream()))
+    return out
+
+
+def glm_dirderiv(X, z, dirs, w=None, family='logistic', out=None):
+    """out = X^T ( w .* b^{(q+1)}(z) .* prod_j X dirs[j] ) for dirs of shape (q, D)."""
+    lib = _cabi.require_cuda()
+    _mat(X, 'X')
+    N, D = X.shape
+    dirs = _f64(dirs, 'dirs').contiguous()
+    if dirs.dim() != 2 or dirs.shape[1] != D:
+        raise ValueError('dirs must have shape (q, D)')
+    if out is None:
+        out = torch.empty(D, dtype=torch.float64, device=X.device)
+    ws, wsb = _ws('glm', lib.vt_glm_workspace_bytes(D), X.device)
+    check(lib.vt_glm_dirderiv(ptr(X), _ld(X), N, D, ptr(_f64(z, 'z')), ptr(w), _cabi.GLM_FAMILIES[family],
+                              ptr(dirs), dirs.shape[0], ptr(out), ptr(ws), wsb, stream()))
+    return out
+
+
+# --------------------------------------------------------------- Cholesky ----
+class CholeskyFactor:
+    """Lower Cholesky factor of a dense SPD matrix, resident on the GPU.
+
+    The analogue of the ``(c, lower)`` tuple of ``scipy.linalg.cho_factor``
+    that the reference stores (``solver_lib.py:26-27``)."""
+
+    def __init__(self, L, dinv):
+        self.L = L
+        self.dinv = dinv
+        self.dim = L.shape[0]
+
+    def solve(self, B, overwrite=False):
+        """(L L^T)^{-1} B for B of shape (D,) or (D, K); float64 CUDA tensor."""
+        lib = _cabi.require_cuda()
+        _f64(B, 'B')
+        vec = B.dim() == 1
+        if B.shape[0] != self.dim or B.dim() > 2:
+            raise ValueError('right-hand side has shape {}, expected ({},) or ({}, K)'.format(
+                tuple(B.shape), self.dim, self.dim))
+        X = B.reshape(self.dim, -1)
+        if not (overwrite and X.is_contiguous()):
+            X = X.contiguous()
+            if X.data_ptr() == B.data_ptr():
+                X = X.clone()
+        check(lib.vt_potrs(ptr(self.L), _ld(self.L), self.dim, ptr(self.dinv), ptr(X), _ld(X), X.shape[1], stream()))
+        return X.reshape(-1) if vec else X
+
+    def inverse(self):
+        eye = torch.eye(self.dim, dtype=torch.float64, device=self.L.device)
+        return self.solve(eye, overwrite=True)
+
+
+def potrf(H, overwrite=False, check_pd=True):
+    """Cholesky-factor a dense symmetric positive-definite matrix on the GPU.
+    Raises ``numpy.linalg.LinAlgError`` like ``cho_factor`` if H is not PD."""
+    lib = _cabi.require_cuda()
+    _f64(H, 'H')
+    if H.dim() != 2 or H.shape[0] != H.shape[1]:
+        raise ValueError('expected a square matrix')
+    D = H.shape[0]
+    if overwrite and H.is_contiguous():
+        L = H
+    else:
+        L = H.contiguous()
+        if L.data_ptr() == H.data_ptr():
+            L = L.clone()
+    dinv = torch.empty(lib.vt_potrf_dinv_doubles(D), dtype=torch.float64, device=H.device)
+    info = torch.zeros(1, dtype=torch.int32, device=H.device)
+    check(lib.vt_potrf(ptr(L), _ld(L), D, ptr(dinv), ctypes.c_void_p(info.data_ptr()), stream()))
+    if check_pd:
+        i = int(info.item())
+        if i != 0:
+            raise np.linalg.LinAlgError(
+                '{}-th leading minor of the array is not positive definite'.format(i))
+    return CholeskyFactor(L, dinv)
+
+
+# ------------------------------------------------------------- IJ apply ----
+def ij_apply(Hinv, X, resid, out=None):
+    """S (D, N) = -Hinv @ (resid[:, None] * X).T without materialising the
+    cross-Hessian."""
+    lib = _cabi.require_cuda()
+    _mat(Hinv, 'Hinv'); _mat(X, 'X')
+    N, D = X.shape
+    if out is None:
+        out = torch.empty((D, N), dtype=torch.float64, device=X.device)
+    check(lib.vt_ij_apply(ptr(Hinv), _ld(Hinv), ptr(X), _ld(X), N, D, ptr(_f64(resid, 'resid')), ptr(out), _ld(out),
+                          stream()))
+    return out
+
+
+def gemv(A, x, alpha=1.0, y0=None, beta=1.0):
+    """alpha * A @ x + beta * y0 for a row-major (M, N) matrix with N long."""
+    lib = _cabi.require_cuda()
+    _mat(A, 'A')
+    M, N = A.shape
+    y = torch.empty(M, dtype=torch.float64, device=A.device)
+    ws, wsb = _ws('gemv', lib.vt_gemv_workspace_bytes(M, N), A.device)
+    check(lib.vt_gemv(ptr(A), _ld(A), M, N, ptr(_f64(x, 'x').contiguous()), float(alpha), ptr(y0), float(beta),
+                      ptr(y), ptr(ws), wsb, stream()))
+    return y
+
+
+# -------------------------------------------------------------------- CG ----
+def cg_init(b, x, r, state):
+    check(_cabi.require_cuda().vt_cg_init(b.numel(), ptr(b), ptr(x), ptr(r), ptr(state), stream()))
+
+
+def cg_update_p(r, p, state, first):
+    check(_cabi.require_cuda().vt_cg_update_p(r.numel(), ptr(r), ptr(p), ptr(state), int(first), stream()))
+
+
+def cg_update_xr(p, q, x, r, state):
+    check(_cabi.require_cuda().vt_cg_update_xr(p.numel(), ptr(p), ptr(q), ptr(x), ptr(r), ptr(state), stream()))
+
+
+# ------------------------------------------------------------- synthetic ----
+_IH_STD = float(np.sqrt((65536.0 ** 2 - 1.0) / 3.0))
+
+
+def synth_design(seed, row0, nrows, ncols, device, scale=None, out=None):
+    lib = _cabi.require_cuda()
+    if scale is None:
+        scale = 1.0 / (_IH_STD * np.sqrt(float(ncols)))
+    if out is None:
+        out = torch.empty((nrows, ncols), dtype=torch.float64, device=device)
+    check(lib.vt_synth_design(ptr(out), _ld(out), int(row0), int(nrows), int(ncols), int(seed), float(scale), stream()))
+    return out
+
+
+def synth_theta(seed, ncols, device):
+    return synth_design(seed ^ 0x5EED, 1 << 40, 1, ncols, device, scale=1.0 / _IH_STD)[0]
+
+
+def synth_bernoulli(seed, row0, z):
+    lib = _cabi.require_cuda()
+    y = torch.empty_like(z)
+    check(lib.vt_synth_bernoulli(ptr(y), ptr(z), int(row0), z.numel(), int(seed), stream()))
+    return y

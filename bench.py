@@ -1,0 +1,416 @@
+#!/usr/bin/env python3
+"""Headline benchmark: all-observation infinitesimal-jackknife sensitivities for
+logistic regression, N = 10M, D = 1024, float64 (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" is the whole hot path over the whole data set:
+    GLM statistics pass  ->  H = X^T diag(s) X  (-> all-reduce of H)  ->
+    Cholesky factor + inverse  ->  S = -H^{-1} G^T  (D x N, device resident)
+through the public API (HyperparameterSensitivityLinearApproximation on a
+GLMObjective).  Observations are sharded over the ranks (strong scaling of the
+fixed N = 10M problem); the only collective is the all-reduce of the D x D
+Hessian.  Prints ONE JSON line on rank 0 (contract in the task statement).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = 'per-obs IJ sensitivities/sec (logit N=10M,D=1024)'
+UNIT = 'obs/s'
+SEED = 20261017
+FP64_PEAK_FALLBACK_TFLOPS = 37.18      # profiles/fp64_peak_r01.jsonl (tools/fp64_peak.cu on this pool's B200)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=4)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--n-total', type=int, default=10_000_000)
+    ap.add_argument('--dim', type=int, default=1024)
+    ap.add_argument('--cpu-sample', type=int, default=100_000, help='rows of the CPU-baseline sample')
+    ap.add_argument('--e2e-steps', type=int, default=2)
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path on the host cores
+# ---------------------------------------------------------------------------
+
+def cpu_reference_step(n, d, seed=SEED):
+    """One bounded CPU step: closed-form H and cross-Hessian in numpy (autograd
+    assembly cannot run in this image - BASELINE.md section 3), then the
+    reference's own solver path get_cholesky_solver(H)(cross) = cho_factor +
+    cho_solve (solver_lib.py:27,29; sensitivity_lib.py:389,226).  Returns
+    seconds for the n-row sample (data generation excluded)."""
+    from oracle import models, solver_lib as osl
+    X, y, theta_star = models.synth_logistic(seed, n, d)
+    w = np.ones(n)
+    theta = theta_star          # timing does not depend on being at the optimum
+    t0 = time.perf_counter()
+    cf = models.glm_closed_form(X, y, theta, w)
+    solve = osl.get_cholesky_solver(cf['hessian'])
+    S = -1 * solve(cf['cross_hessian'])
+    t1 = time.perf_counter()
+    assert S.shape == (d, n)
+    return t1 - t0
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get('num_threads', 1) for p in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    n, d = args.cpu_sample, args.dim
+    for _ in range(max(args.warmup, 1) if args.warmup < 2 else 1):
+        cpu_reference_step(min(n, 20000), d)
+    times = [cpu_reference_step(n, d) for _ in range(max(1, min(args.steps, 3)))]
+    sec = float(np.median(times))
+    value = n / sec
+    cores = blas_threads()
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': len(times), 'warmup': 1, 'ms_per_step': sec * 1e3 * (args.n_total / n),
+        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'logistic IJ N=10M D=1024 f64 (BASELINE configs[1])', 'n_obs': args.n_total,
+                   'dim': d},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': '{} of {} observations, D={} (cost is linear in N beyond the D^3/3 factorisation); '
+                                   'numpy closed-form assembly + cho_factor/cho_solve'.format(n, args.n_total, d)},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------
+# clock sampling during the timed region
+# ---------------------------------------------------------------------------
+
+class ClockSampler:
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,' \
+        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                 '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            f = [x.strip() for x in r.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(np.max(mx)), 'power_w_max': float(np.max(pw)),
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    import vittles_b200 as vt
+    from vittles_b200 import ops
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus and world > 1:
+        raise SystemExit('--gpus {} but WORLD_SIZE={}'.format(args.gpus, world))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    group = None
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+        group = dist.group.WORLD
+
+    N, D = args.n_total, args.dim
+    r0 = (N * rank) // world
+    r1 = (N * (rank + 1)) // world
+    n_loc = r1 - r0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- synthetic data, generated on the device (counter-based) ------------
+    X = ops.synth_design(SEED, r0, n_loc, D, dev)
+    theta_star = ops.synth_theta(SEED, D, dev)
+    zeros = torch.zeros(n_loc, dtype=torch.float64, device=dev)
+    z_star = ops.glm_stats(X, theta_star, zeros, None, 'logistic', want_grad=False)[0]
+    y = ops.synth_bernoulli(SEED, r0, z_star)
+    del z_star, zeros
+    w = torch.ones(n_loc, dtype=torch.float64, device=dev)
+    obj = vt.objectives.GLMObjective(X, y, family='logistic', group=group)
+
+    # ---- optimum by Newton's method on the same kernels (setup, untimed) ----
+    theta = torch.zeros(D, dtype=torch.float64, device=dev)
+    for it in range(25):
+        st = obj.vt_stats(theta, w)
+        H = obj.vt_hessian(theta, w, st)
+        step = ops.potrf(H, overwrite=True).solve(st['grad'])
+        theta = theta - step
+        if float(torch.linalg.vector_norm(step)) < 1e-11:
+            break
+    grad_norm = float(torch.linalg.vector_norm(obj.vt_stats(theta, w)['grad']))
+    del st, H, step
+
+    def one_step():
+        sens = vt.HyperparameterSensitivityLinearApproximation(obj, theta, w)
+        return sens
+
+    peak_tflops = ops.fp64_peak_probe(0.25)
+
+    # ---- timed region: device-resident inputs --------------------------------
+    for _ in range(args.warmup):
+        s_ = one_step(); del s_
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        s_ = one_step(); del s_
+    e1.record()
+    barrier()
+    launches = ops.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms.item()) / args.steps
+    value = N / (ms_per_step * 1e-3)
+
+    # ---- per-kernel timing (same stream, CUDA events) -> roofline ------------
+    def timed(fn, reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        out = fn()
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(reps):
+            del out
+            out = fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps, out
+    reps = max(2, min(args.steps, 3))
+    t_stats, st = timed(lambda: obj.vt_stats(theta, w), reps)
+    t_syrk, H = timed(lambda: ops.syrk_weighted(X, st['s']), reps)
+    if world > 1:
+        dist.all_reduce(H)
+    t_chol, hinv = timed(lambda: ops.potrf(H).inverse(), reps)
+    t_apply, S = timed(lambda: ops.ij_apply(hinv, X, st['resid']), reps)
+    apply_tflops = 2.0 * D * D * n_loc / (t_apply * 1e-3) / 1e12
+    syrk_tflops = float(D) * (D + 1) * n_loc / (t_syrk * 1e-3) / 1e12
+    stats_gbs = 8.0 * D * n_loc / (t_stats * 1e-3) / 1e9
+
+    # size-independent correctness properties at full size (sampled columns)
+    idx = torch.randint(0, n_loc, (256,), device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+    G_cols = (X[idx] * st['resid'][idx, None]).T.contiguous()                # (D, 256)
+    resid_check = ops.gemm(H, S[:, idx].contiguous().T.contiguous(), 'KC', 'KC') + G_cols
+    rel_resid = float(torch.max(torch.abs(resid_check)) / torch.max(torch.abs(G_cols)))
+    del S, G_cols, resid_check
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
+            traffic = json.load(f).get('ij_apply_dram_bytes_per_launch')
+    except Exception:
+        pass
+
+    # ---- end to end: HOST buffers in, host result out ---------------------------
+    e2e = None
+    if not args.no_e2e:
+        try:
+            host = stage_to_host(torch, X, y, theta)
+            # free every device-resident tensor of the resident phase: the e2e step brings its own
+            obj.X = obj.y = obj = None
+            del X, y, st, H, hinv, w
+            ops.free_workspaces()
+            torch.cuda.empty_cache()
+            e2e = run_e2e(args, vt, torch, dist, dev, group, world, host)
+        except Exception as exc:      # report, never hide
+            e2e = {'value': None, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0,
+                   'error': repr(exc)[:300]}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_s = args.cpu_sample
+        cpu_reference_step(min(n_s, 20000), D)
+        sec = cpu_reference_step(n_s, D)
+        cpu_baseline = {'value': n_s / sec, 'unit': UNIT, 'cores': blas_threads(), 'kind': 'port',
+                        'sample': '{} of {} observations, D={}; numpy closed-form assembly + '
+                                  'cho_factor/cho_solve (oracle port of the reference path)'.format(n_s, N, D)}
+
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': 'logistic IJ N=10M D=1024 f64 (BASELINE configs[1])', 'n_obs': N, 'dim': D,
+                       'sharding': 'observations over {} rank(s), one all-reduce of the DxD Hessian'.format(world),
+                       'l2': 'inputs ({:.1f} GB per rank) exceed the 126 MB L2'.format(8.0 * n_loc * D / 1e9),
+                       'grad_norm_at_opt': grad_norm, 'sampled_residual_rel': rel_resid},
+            'clocks': clocks,
+            'gpu_launches': launches,
+            'roofline': {'bound': 'tensor', 'kernel': 'dgemm_kernel<KC,KC> (vt_ij_apply: S = -Hinv G^T)',
+                         'achieved': apply_tflops, 'peak': peak_tflops, 'unit': 'TFLOP/s',
+                         'frac': apply_tflops / peak_tflops,
+                         'peak_source': 'FP64 DMMA probe measured in this run (vt_fp64_peak_probe); '
+                                        'MEASURED_PEAKS.json has no FP64 entry; tools/fp64_peak.cu gave '
+                                        '{} TFLOP/s'.format(FP64_PEAK_FALLBACK_TFLOPS),
+                         'traffic': traffic,
+                         'algorithmic': '2*D^2 flop per observation'},
+            'kernels': {
+                'ij_apply': {'ms': t_apply, 'tflops': apply_tflops, 'frac_fp64_peak': apply_tflops / peak_tflops},
+                'syrk_weighted': {'ms': t_syrk, 'tflops_algorithmic_D(D+1)': syrk_tflops,
+                                  'frac_fp64_peak': syrk_tflops / peak_tflops},
+                'glm_stats': {'ms': t_stats, 'gb_per_s': stats_gbs,
+                              'frac_hbm_peak': stats_gbs / peaks['hbm_gbs'] if 'hbm_gbs' in peaks else None},
+                'potrf_plus_inverse': {'ms': t_chol},
+            },
+            'cpu_baseline': cpu_baseline,
+            'e2e': e2e,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def stage_to_host(torch, X, y, theta):
+    """Pinned host copies of this rank's inputs (set-up for the e2e leg)."""
+    n_loc, D = X.shape
+    X_host = torch.empty((n_loc, D), dtype=torch.float64, pin_memory=True)
+    X_host.copy_(X)
+    y_host = torch.empty(n_loc, dtype=torch.float64, pin_memory=True)
+    y_host.copy_(y)
+    w_host = torch.ones(n_loc, dtype=torch.float64).pin_memory()
+    w1 = torch.ones(n_loc, dtype=torch.float64)
+    w1[::7] = 0.0
+    return dict(X=X_host, y=y_host, w=w_host, w1=w1.pin_memory(), theta=theta.cpu().pin_memory())
+
+
+def run_e2e(args, vt, torch, dist, dev, group, world, host):
+    """The same metric through the public API with HOST buffers: every step
+    copies this rank's X, y, w and theta from pinned host memory to the device,
+    runs the whole path, and reads the result summary (the linear-approximation
+    prediction for a leave-k-out weight vector, D doubles, plus the D x D
+    Hessian) back to the host.  The (D, N) sensitivity matrix itself stays on
+    the device, as a user of an 82 GB result would keep it."""
+    X_host, y_host, w_host, w1_host, theta_host = host['X'], host['y'], host['w'], host['w1'], host['theta']
+    n_loc, D = X_host.shape
+    N = args.n_total
+    h2d = (X_host.numel() + y_host.numel() + 2 * w_host.numel() + theta_host.numel()) * 8
+    d2h = (D + D * D) * 8
+
+    def step():
+        Xd = X_host.to(dev, non_blocking=True)
+        yd = y_host.to(dev, non_blocking=True)
+        wd = w_host.to(dev, non_blocking=True)
+        w1d = w1_host.to(dev, non_blocking=True)
+        td = theta_host.to(dev, non_blocking=True)
+        o = vt.objectives.GLMObjective(Xd, yd, family='logistic', group=group)
+        sens = vt.HyperparameterSensitivityLinearApproximation(o, td, wd)
+        pred = sens.predict_opt_par_from_hyper_par(w1d).cpu()
+        hess = sens.get_hessian_at_opt().cpu()
+        return pred, hess
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    out = step(); del out
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        out = step(); del out
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    ms = torch.tensor([max(e0.elapsed_time(e1), wall * 1e3)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = float(ms.item()) / args.e2e_steps
+    return {'value': N / (ms_step * 1e-3), 'unit': UNIT, 'ms_per_step': ms_step, 'steps': args.e2e_steps,
+            'h2d_bytes_per_step': h2d * world, 'd2h_bytes_per_step': d2h * world,
+            'api': 'HyperparameterSensitivityLinearApproximation(GLMObjective(host X, host y), theta, w)'
+                   '.predict_opt_par_from_hyper_par(w1) + get_hessian_at_opt()'}
+
+
+if __name__ == '__main__':
+    main()

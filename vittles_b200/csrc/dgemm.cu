@@ -1,5 +1,6 @@
 // FP64 DMMA GEMM engine - see dgemm.cuh for the design notes.
 #include "dgemm.cuh"
+#include <cstdlib>
 
 namespace vt {
 
@@ -8,7 +9,6 @@ namespace {
 struct Unit {
   int m0, n0;      // tile origin
   int kit0, nkit;  // k-iteration range of this unit
-  long slot;       // workspace slot (split-K)
 };
 
 __device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int& tm, int& tn) {
@@ -35,61 +35,60 @@ __device__ __forceinline__ Unit decode_unit(const GemmParams& p, long u) {
   const int q = p.kiters / p.parts, rem = p.kiters % p.parts;
   r.kit0 = part * q + min(part, rem);
   r.nkit = q + (part < rem ? 1 : 0);
-  r.slot = u;
   return r;
 }
 
-// Stage one operand tile (128 rows x 16 k) into shared memory.
-template <int MODE>
-__device__ __forceinline__ void issue_tile(double* __restrict__ s, const double* __restrict__ gp, long ld,
-                                           int r0, int R, int k0, int K, int vec, int tid) {
-  if (MODE == KC) {
-    if (vec) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int c = tid + i * GEMM_THREADS;
-        const int row = c >> 3, ch = c & 7;
-        const int gr = r0 + row, gk = k0 + ch * 2;
-        int bytes = (gr < R) ? min(max((K - gk) * 8, 0), 16) : 0;
-        const double* src = bytes ? gp + (long)gr * ld + gk : gp;
-        cp_async16(s + row * LDKC + ch * 2, src, bytes);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int e = tid + i * GEMM_THREADS;
-        const int row = e >> 4, kc = e & 15;
-        const int gr = r0 + row, gk = k0 + kc;
-        const bool ok = (gr < R) && (gk < K);
-        cp_async8(s + row * LDKC + kc, ok ? gp + (long)gr * ld + gk : gp, ok ? 8 : 0);
-      }
-    }
+// Kernel configuration: warp grid over the 128x128 CTA tile and whether the
+// DMMA fragments are double buffered in registers.
+template <int WARPS_M_, int WARPS_N_, bool DBUF_>
+struct GemmCfg {
+  static constexpr int WARPS_M = WARPS_M_, WARPS_N = WARPS_N_;
+  static constexpr int NTHREADS = WARPS_M_ * WARPS_N_ * 32;
+  static constexpr int MT = BM / (WARPS_M_ * 8), NT = BN / (WARPS_N_ * 8);
+  static constexpr int VC = (BM * BK / 2) / NTHREADS;   // 16-byte chunks per operand per thread per stage
+  static constexpr bool DBUF = DBUF_;
+};
+
+// Copy one 16-byte chunk (VEC) or two 8-byte elements (!VEC: odd leading
+// dimension or unaligned base) of an operand tile (128 rows x 16 k) into shared
+// memory; `chunk` in [0, VC).  Straight-line and fully predicated (zero fill
+// outside the matrix or when `live` is false) so that ptxas can interleave the
+// copies with the DMMA stream: a runtime branch per chunk splits the hot loop
+// into dozens of basic blocks and costs ~20% of the tensor pipe (r01 tuning).
+template <int MODE, bool VEC, int NTHREADS>
+__device__ __forceinline__ void issue_chunk(double* __restrict__ s, const double* __restrict__ gp, long ld, int r0,
+                                            int R, int k0, int K, bool live, int tid, int chunk) {
+  if (VEC) {
+    const int c = tid + chunk * NTHREADS;
+    int row, kc, sm_off;
+    if (MODE == KC) { row = c >> 3; kc = (c & 7) * 2; sm_off = row * LDKC + kc; }
+    else            { kc = c >> 6; row = (c & 63) * 2; sm_off = kc * LDKS + row; }
+    const int gr = r0 + row, gk = k0 + kc;
+    // contiguous direction: k for KC, row for KS
+    const int left = (MODE == KC) ? (K - gk) : (R - gr);
+    const bool other_ok = (MODE == KC) ? (gr < R) : (gk < K);
+    const int bytes = (live && other_ok) ? min(max(left * 8, 0), 16) : 0;
+    const long off = (MODE == KC) ? (long)gr * ld + gk : (long)gk * ld + gr;
+    cp_async16(s + sm_off, bytes ? gp + off : gp, bytes);
   } else {
-    if (vec) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int c = tid + i * GEMM_THREADS;
-        const int krow = c >> 6, ch = c & 63;
-        const int gk = k0 + krow, gr = r0 + ch * 2;
-        int bytes = (gk < K) ? min(max((R - gr) * 8, 0), 16) : 0;
-        const double* src = bytes ? gp + (long)gk * ld + gr : gp;
-        cp_async16(s + krow * LDKS + ch * 2, src, bytes);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int e = tid + i * GEMM_THREADS;
-        const int krow = e >> 7, r = e & 127;
-        const int gk = k0 + krow, gr = r0 + r;
-        const bool ok = (gr < R) && (gk < K);
-        cp_async8(s + krow * LDKS + r, ok ? gp + (long)gk * ld + gr : gp, ok ? 8 : 0);
-      }
+    for (int i = 0; i < 2; ++i) {
+      const int e = tid + (2 * chunk + i) * NTHREADS;
+      int row, kc, sm_off;
+      if (MODE == KC) { row = e >> 4; kc = e & 15; sm_off = row * LDKC + kc; }
+      else            { kc = e >> 7; row = e & 127; sm_off = kc * LDKS + row; }
+      const int gr = r0 + row, gk = k0 + kc;
+      const bool ok = live && (gr < R) && (gk < K);
+      const long off = (MODE == KC) ? (long)gr * ld + gk : (long)gk * ld + gr;
+      cp_async8(s + sm_off, ok ? gp + off : gp, ok ? 8 : 0);
     }
   }
 }
 
-template <int AMODE, int BMODE, bool KSCALE>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_kernel(const GemmParams p) {
+template <int AMODE, int BMODE, bool KSCALE, bool VEC, class CFG>
+__global__ void __launch_bounds__(CFG::NTHREADS, 1) dgemm_kernel(const GemmParams p) {
+  constexpr int MT = CFG::MT, NT = CFG::NT, NTHREADS = CFG::NTHREADS, VC = CFG::VC;
+  constexpr int WM = MT * 8, WN = NT * 8;
   extern __shared__ __align__(16) double smem[];
   double* sA = smem;
   double* sB = smem + STAGES * TILE_DOUBLES;
@@ -98,8 +97,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_kernel(const GemmParams
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, tig = lane & 3;
-  const int wm0 = (warp >> 2) * WM;   // 2 warps along M
-  const int wn0 = (warp & 3) * WN;    // 4 warps along N
+  const int wm0 = (warp / CFG::WARPS_N) * WM;
+  const int wn0 = (warp % CFG::WARPS_N) * WN;
 
   // fragment base offsets inside a stage
   const int a_off = (AMODE == KC) ? (wm0 + g) * LDKC + tig : tig * LDKS + wm0 + g;
@@ -125,60 +124,108 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_kernel(const GemmParams
   Unit mU = lU;
   int mk = 0;
 
-  auto issue_next = [&](int stage) {
-    if (lvalid) {
-      const int k0 = (lU.kit0 + lk) * BK;
-      issue_tile<AMODE>(sA + stage * TILE_DOUBLES, p.A, p.lda, lU.m0, p.M, k0, p.K, p.a_vec, tid);
-      issue_tile<BMODE>(sB + stage * TILE_DOUBLES, p.B, p.ldb, lU.n0, p.N, k0, p.K, p.b_vec, tid);
-      if (KSCALE && tid < BK) {
-        const bool ok = k0 + tid < p.K;
-        cp_async8(sS + stage * BK + tid, ok ? p.kscale + k0 + tid : p.kscale, ok ? 8 : 0);
-      }
-      if (++lk == lU.nkit) {
-        lk = 0;
-        lu += gridDim.x;
-        lvalid = lu < total_units;
-        if (lvalid) lU = decode_unit(p, lu);
-      }
+  constexpr int KK = BK / 4;
+  constexpr int SLOTS = 2 * VC;                      // copy slots per thread per stage: A chunks then B chunks
+  constexpr int SPK = (SLOTS + KK - 2) / (KK - 1);   // slots per k4 step; the refill is spread over steps 0..KK-2
+  // copy slots [first, last) of the refill of `stage` at the load cursor (straight-line, predicated)
+  auto issue_slots = [&](int stage, int first, int last) {
+    const int k0 = (lU.kit0 + lk) * BK;
+#pragma unroll
+    for (int sl = first; sl < last; ++sl) {
+      if (sl < VC)
+        issue_chunk<AMODE, VEC, NTHREADS>(sA + stage * TILE_DOUBLES, p.A, p.lda, lU.m0, p.M, k0, p.K, lvalid, tid, sl);
+      else if (sl < SLOTS)
+        issue_chunk<BMODE, VEC, NTHREADS>(sB + stage * TILE_DOUBLES, p.B, p.ldb, lU.n0, p.N, k0, p.K, lvalid, tid,
+                                          sl - VC);
+    }
+  };
+  // per-k scale vector of the stage, then close the cp.async group
+  auto finish_refill = [&](int stage) {
+    if (KSCALE && tid < BK) {
+      const int k = (lU.kit0 + lk) * BK + tid;
+      const bool ok = lvalid && k < p.K;
+      cp_async8(sS + stage * BK + tid, ok ? p.kscale + k : p.kscale, ok ? 8 : 0);
     }
     cp_async_commit();
   };
+  auto advance_load_cursor = [&]() {
+    if (lvalid && ++lk == lU.nkit) {
+      lk = 0;
+      lu += gridDim.x;
+      lvalid = lu < total_units;
+      if (lvalid) lU = decode_unit(p, lu);
+    }
+  };
 
 #pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) issue_next(s);
+  for (int s = 0; s < STAGES - 1; ++s) {
+    issue_slots(s, 0, SLOTS);
+    finish_refill(s);
+    advance_load_cursor();
+  }
+
+  // Register (double) buffer for the DMMA fragments: the fragments of k4-step
+  // kk+1 (or of the next stage's step 0) are loaded while the DMMAs of step kk
+  // are in the tensor pipe.
+  constexpr int NBUF = CFG::DBUF ? 2 : 1;
+  double fa[NBUF][MT], fb[NBUF][NT], fs[NBUF];
+  auto load_frags = [&](int buf, int stg, int kk) {
+    const double* As = sA + stg * TILE_DOUBLES + a_off + kk * A_KK;
+    const double* Bs = sB + stg * TILE_DOUBLES + b_off + kk * B_KK;
+#pragma unroll
+    for (int i = 0; i < MT; ++i) fa[buf][i] = As[i * A_MT];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) fb[buf][j] = Bs[j * B_NT];
+    if (KSCALE) fs[buf] = sS[stg * BK + kk * 4 + tig];
+  };
+
+  cp_async_wait<STAGES - 2>();
+  __syncthreads();
+  if (CFG::DBUF) load_frags(0, 0, 0);
 
   int stage = 0;
   while (mvalid) {
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();
-    issue_next((stage + STAGES - 1) % STAGES);
-
-    const double* As = sA + stage * TILE_DOUBLES + a_off;
-    const double* Bs = sB + stage * TILE_DOUBLES + b_off;
-    const double* Ss = sS + stage * BK + tig;
+    const int refill_stage = (stage + STAGES - 1) % STAGES;
 #pragma unroll
-    for (int kk = 0; kk < BK / 4; ++kk) {
-      double a[MT], b[NT];
-#pragma unroll
-      for (int i = 0; i < MT; ++i) a[i] = As[i * A_MT + kk * A_KK];
-#pragma unroll
-      for (int j = 0; j < NT; ++j) b[j] = Bs[j * B_NT + kk * B_KK];
+    for (int kk = 0; kk < KK; ++kk) {
+      const int cur = CFG::DBUF ? (kk & 1) : 0, nxt = CFG::DBUF ? (cur ^ 1) : 0;
+      if (!CFG::DBUF) load_frags(0, stage, kk);
+      if (CFG::DBUF) {
+        if (kk == KK - 1) {
+          // the next stage must have landed (own copies) and be visible (barrier);
+          // the barrier also certifies that every warp is done reading the stage
+          // that the next iteration's refill will overwrite
+          cp_async_wait<STAGES - 2>();
+          __syncthreads();
+          load_frags(nxt, (stage + 1) % STAGES, 0);
+        } else {
+          load_frags(nxt, stage, kk + 1);
+        }
+      }
+      // refill of the stage consumed in the previous iteration, spread over
+      // steps 0..KK-2 and placed after the fragment loads in program order
+      if (kk < KK - 1) issue_slots(refill_stage, kk * SPK, (kk + 1) * SPK);
+      if (kk == KK - 2) finish_refill(refill_stage);
       if (KSCALE) {
-        const double sc = Ss[kk * 4];
 #pragma unroll
-        for (int j = 0; j < NT; ++j) b[j] *= sc;
+        for (int j = 0; j < NT; ++j) fb[cur][j] *= fs[cur];
       }
 #pragma unroll
       for (int i = 0; i < MT; ++i)
 #pragma unroll
-        for (int j = 0; j < NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        for (int j = 0; j < NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[cur][i], fb[cur][j]);
     }
+    if (!CFG::DBUF) {
+      cp_async_wait<STAGES - 2>();
+      __syncthreads();
+    }
+    advance_load_cursor();
     stage = (stage + 1) % STAGES;
 
     if (++mk == mU.nkit) {
       // ------------------------------------------------------ epilogue ----
       if (p.parts > 1) {
-        double* ws = p.workspace + mU.slot * (long)(BM * BN);
+        double* ws = p.workspace + mu * (long)(BM * BN);
 #pragma unroll
         for (int i = 0; i < MT; ++i)
 #pragma unroll
@@ -274,13 +321,42 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmParams p) 
   if (p.lower && p.mirror && r != c) p.C[(long)c * p.ldc + r] = v;
 }
 
-template <int AMODE, int BMODE, bool KSCALE>
-int launch_variant(const GemmParams& p, int grid, cudaStream_t stream) {
-  VT_CUDA(cudaFuncSetAttribute(dgemm_kernel<AMODE, BMODE, KSCALE>,
+template <int AMODE, int BMODE, bool KSCALE, bool VEC, class CFG>
+int launch_cfg(const GemmParams& p, int grid, cudaStream_t stream) {
+  VT_CUDA(cudaFuncSetAttribute(dgemm_kernel<AMODE, BMODE, KSCALE, VEC, CFG>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  dgemm_kernel<AMODE, BMODE, KSCALE><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(p);
+  dgemm_kernel<AMODE, BMODE, KSCALE, VEC, CFG><<<grid, CFG::NTHREADS, GEMM_SMEM_BYTES, stream>>>(p);
   VT_LAUNCH_CHECK();
   return VT_OK;
+}
+
+using CfgDefault = GemmCfg<2, 4, true>;
+
+// VT_GEMM_CFG selects an alternative kernel configuration (tuning builds only).
+int tuning_cfg() {
+  static int cfg = -1;
+  if (cfg < 0) {
+    const char* e = getenv("VT_GEMM_CFG");
+    cfg = e ? atoi(e) : 0;
+  }
+  return cfg;
+}
+
+template <int AMODE, int BMODE, bool KSCALE>
+int launch_variant(const GemmParams& p, int grid, cudaStream_t stream) {
+  const bool vec = p.a_vec && p.b_vec;
+#ifdef VT_GEMM_TUNING
+  if (vec) {
+    switch (tuning_cfg()) {
+      case 1: return launch_cfg<AMODE, BMODE, KSCALE, true, GemmCfg<4, 4, true>>(p, grid, stream);
+      case 2: return launch_cfg<AMODE, BMODE, KSCALE, true, GemmCfg<4, 4, false>>(p, grid, stream);
+      case 3: return launch_cfg<AMODE, BMODE, KSCALE, true, GemmCfg<2, 4, false>>(p, grid, stream);
+      default: break;
+    }
+  }
+#endif
+  if (vec) return launch_cfg<AMODE, BMODE, KSCALE, true, CfgDefault>(p, grid, stream);
+  return launch_cfg<AMODE, BMODE, KSCALE, false, CfgDefault>(p, grid, stream);
 }
 
 }  // namespace

@@ -28,9 +28,6 @@ namespace vt {
 enum OpMode : int { KC = 0, KS = 1 };
 
 constexpr int BM = 128, BN = 128, BK = 16;
-constexpr int GEMM_THREADS = 256;
-constexpr int WM = 64, WN = 32;
-constexpr int MT = WM / 8, NT = WN / 8;
 constexpr int LDKC = BK + 4;    // 20 doubles
 constexpr int LDKS = BM + 4;    // 132 doubles
 constexpr int TILE_DOUBLES = BM * LDKC;  // 2560 >= BK*LDKS = 2112

@@ -127,6 +127,31 @@ int vt_cg_init(int D, const double* b, double* x, double* r, double* state, void
 int vt_cg_update_p(int D, const double* r, double* p, double* state, int first, void* stream);
 int vt_cg_update_xr(int D, const double* p, const double* q, double* x, double* r, double* state, void* stream);
 
+/* ---- Block-arrow Hessians (SparseBlockHessian) ------------------------------
+ * H = [blockdiag(B_g) C; C^T Hgg], B_g (M x M, M <= 32), C_g (M x Dg): the
+ * structure sparse_hessian_lib.py:69-168 assembles entry by entry and
+ * solver_lib.py:46-48 hands to SuperLU.  Factorisation on the GPU:
+ *   L_g = chol(B_g) (vt_block_potrf_batched), Z_g = L_g^{-1} C_g
+ *   (vt_block_trsm_batched, in place), Schur = Hgg - Z^T Z (vt_syrk_weighted on
+ *   the (G*M) x Dg matrix Z) and vt_potrf of the Schur complement; the solve
+ *   uses vt_block_solve_batched (mode 0: L^{-1}, 1: L^{-T}), vt_tall_colsum
+ *   (Z^T u) and vt_tall_gemv (Z x).  *info: 0 or 1 + index of a non-PD block.
+ * vt_gmm_blocks assembles B_g, C_g, the responsibilities r (N x K), the local
+ * gradient and the per-observation objective terms in closed form for the
+ * Gaussian-mixture mean-field VB objective (benchmark config 3); any output
+ * pointer may be NULL.                                                       */
+int vt_block_potrf_batched(double* blocks, int64_t G, int M, int32_t* info, void* stream);
+int vt_block_trsm_batched(const double* Lb, double* C, int64_t G, int M, int Dg, void* stream);
+int vt_block_solve_batched(const double* Lb, double* b, int64_t G, int M, int mode, void* stream);
+int vt_tall_gemv(const double* Z, int64_t R, int Dg, const double* x, double alpha, double* y, double beta,
+                 void* stream);
+size_t vt_tall_colsum_workspace_bytes(int Dg);
+int vt_tall_colsum(const double* Z, int64_t R, int Dg, const double* u, double alpha, const double* y0, double beta,
+                   double* out, void* workspace, size_t workspace_bytes, void* stream);
+int vt_gmm_blocks(const double* X, int64_t N, int d, int K, const double* m, const double* rho,
+                  const double* log_pi, double* blocks, double* cross, double* rmat, double* grad_rho,
+                  double* obj_terms, void* stream);
+
 /* ---- Synthetic data (bench and tests) ---------------------------------------
  * Counter-based, reproducible for any row range (oracle twin:
  * oracle/models.py synth_design / synth_uniform).                            */

@@ -86,8 +86,8 @@ class QuadraticModel:
 def _psd_from_free(free6):
     """3x3 PSD matrix from 6 free numbers: Cholesky factor with a log diagonal
     (the shape of paragami's PSDSymmetricMatrixPattern free map)."""
-    L = torch.zeros(3, 3, dtype=free6.dtype)
-    idx = torch.tril_indices(3, 3)
+    L = torch.zeros(3, 3, dtype=free6.dtype, device=free6.device)
+    idx = torch.tril_indices(3, 3, device=free6.device)
     L = L.index_put((idx[0], idx[1]), free6)
     d = torch.diagonal(L)
     L = L - torch.diag(d) + torch.diag(torch.exp(d))

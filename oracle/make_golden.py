@@ -303,7 +303,8 @@ def golden_sparse_hessian():
     centers = rng.normal(size=(K, d)) * 3
     Xobs = centers[rng.randint(K, size=N)] + rng.normal(size=(N, d))
     fg = models.gmm_vb_objective(Xobs, K)
-    xg = np.concatenate([centers.reshape(-1) + 0.1 * rng.normal(size=K * d), 0.5 * rng.normal(size=N * (K - 1))])
+    xg = models.gmm_vb_fit(Xobs, K)                      # at the VB optimum: H is positive definite
+    assert np.linalg.norm(torch.func.grad(fg)(torch.as_tensor(xg)).numpy()) < 1e-8
     indsg = models.gmm_vb_sparsity(N, K, d)
     shg = vittles.SparseBlockHessian(fg, indsg)
     hgm = np.array(shg.get_hessian(xg).todense())

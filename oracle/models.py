@@ -226,3 +226,24 @@ def mvn_kl_closed_form(true_mean, true_info):
     H[:dim, :dim] = true_info
     H[dim:, dim:] = np.diag(0.5 / var ** 2)
     return np.concatenate([np.asarray(true_mean, dtype=np.float64), var]), H
+
+
+def gmm_vb_fit(Xobs, K, prior_prec=1e-2, iters=200, seed=0, log_pi=None):
+    """Coordinate ascent for the GMM-VB objective (closed-form updates):
+    rho_n = optimal logits given m, m_k = sum_n r_nk x_n / (sum_n r_nk + prior).
+    Returns the flat parameter at (numerically) the optimum, where the Hessian
+    is positive definite."""
+    Xobs = np.asarray(Xobs, dtype=np.float64)
+    N, d = Xobs.shape
+    rng = np.random.RandomState(seed)
+    lp = -np.log(K) * np.ones(K) if log_pi is None else np.asarray(log_pi)
+    m = Xobs[rng.choice(N, K, replace=False)].copy()
+    for _ in range(iters):
+        c = 0.5 * ((Xobs[:, None, :] - m[None]) ** 2).sum(-1) - lp[None]
+        logits = -(c - c[:, -1:])
+        r = np.exp(logits - logits.max(1, keepdims=True))
+        r /= r.sum(1, keepdims=True)
+        m = (r.T @ Xobs) / (r.sum(0)[:, None] + prior_prec)
+    c = 0.5 * ((Xobs[:, None, :] - m[None]) ** 2).sum(-1) - lp[None]
+    logits = -(c - c[:, -1:])
+    return np.concatenate([m.reshape(-1), logits[:, :K - 1].reshape(-1)])

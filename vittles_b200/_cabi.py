@@ -45,6 +45,13 @@ SIGNATURES = {
     'vt_cg_init': (_I, [_I, _P, _P, _P, _P, _P]),
     'vt_cg_update_p': (_I, [_I, _P, _P, _P, _I, _P]),
     'vt_cg_update_xr': (_I, [_I, _P, _P, _P, _P, _P, _P]),
+    'vt_block_potrf_batched': (_I, [_P, _I64, _I, _P, _P]),
+    'vt_block_trsm_batched': (_I, [_P, _P, _I64, _I, _I, _P]),
+    'vt_block_solve_batched': (_I, [_P, _P, _I64, _I, _I, _P]),
+    'vt_tall_gemv': (_I, [_P, _I64, _I, _P, _D, _P, _D, _P]),
+    'vt_tall_colsum_workspace_bytes': (_SZ, [_I]),
+    'vt_tall_colsum': (_I, [_P, _I64, _I, _P, _D, _P, _D, _P, _P, _SZ, _P]),
+    'vt_gmm_blocks': (_I, [_P, _I64, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'vt_synth_design': (_I, [_P, _I64, _I64, _I64, _I, _U64, _D, _P]),
     'vt_synth_uniform': (_I, [_P, _I64, _I64, _U64, _P]),
     'vt_synth_bernoulli': (_I, [_P, _P, _I64, _I64, _U64, _P]),

@@ -1,5 +1,6 @@
 // extern "C" entry points declared in include/vittles_b200.h.
 #include "../../include/vittles_b200.h"
+#include "blockchol.cuh"
 #include "chol.cuh"
 #include "common.cuh"
 #include "dgemm.cuh"
@@ -195,6 +196,30 @@ int vt_cg_update_p(int D, const double* r, double* p, double* state, int first, 
 }
 int vt_cg_update_xr(int D, const double* p, const double* q, double* x, double* r, double* state, void* stream) {
   return cg_update_xr(D, p, q, x, r, state, S(stream));
+}
+
+int vt_block_potrf_batched(double* blocks, int64_t G, int M, int32_t* info, void* stream) {
+  return block_potrf(blocks, G, M, info, S(stream));
+}
+int vt_block_trsm_batched(const double* Lb, double* C, int64_t G, int M, int Dg, void* stream) {
+  return block_trsm(Lb, C, G, M, Dg, S(stream));
+}
+int vt_block_solve_batched(const double* Lb, double* b, int64_t G, int M, int mode, void* stream) {
+  return block_solve(Lb, b, G, M, mode, S(stream));
+}
+int vt_tall_gemv(const double* Z, int64_t R, int Dg, const double* x, double alpha, double* y, double beta,
+                 void* stream) {
+  return tall_gemv(Z, R, Dg, x, alpha, y, beta, S(stream));
+}
+size_t vt_tall_colsum_workspace_bytes(int Dg) { return tall_colsum_workspace_bytes(Dg); }
+int vt_tall_colsum(const double* Z, int64_t R, int Dg, const double* u, double alpha, const double* y0, double beta,
+                   double* out, void* workspace, size_t workspace_bytes, void* stream) {
+  return tall_colsum(Z, R, Dg, u, alpha, y0, beta, out, static_cast<double*>(workspace), workspace_bytes, S(stream));
+}
+int vt_gmm_blocks(const double* X, int64_t N, int d, int K, const double* m, const double* rho,
+                  const double* log_pi, double* blocks, double* cross, double* rmat, double* grad_rho,
+                  double* obj_terms, void* stream) {
+  return gmm_blocks(X, N, d, K, m, rho, log_pi, blocks, cross, rmat, grad_rho, obj_terms, S(stream));
 }
 
 int vt_synth_design(double* X, int64_t ldx, int64_t row0, int64_t nrows, int ncols, uint64_t seed, double scale,

@@ -205,3 +205,70 @@ class GLMPriorObjective(StructuredObjective):
         elif m == 1:
             out = out + tau * p0 * to_device(eta_dirs[0], dev)
         return out
+
+
+class GMMVBObjective(StructuredObjective):
+    """Mean-field VB for a Gaussian mixture with unit covariances, with
+    per-observation local parameters (benchmark config 3).  Flat parameter
+
+        x = ( m (K*d global means),  rho_1 .. rho_N (K-1 free logits each) )
+
+        r_n = softmax([rho_n, 0]),  c_nk = |x_n - m_k|^2 / 2 - log pi_k
+        f(x) = sum_n sum_k r_nk (c_nk + log r_nk) + prior_prec/2 * |m|^2
+
+    The Hessian is block-arrow: (K-1)x(K-1) local blocks, (K-1)x(K*d) cross
+    blocks, and a diagonal global block.  ``vt_block_hessian`` assembles all of
+    it in closed form in one kernel pass (``vt_gmm_blocks``)."""
+
+    def __init__(self, X, K, log_pi=None, prior_prec=1e-2, device=None, group=None):
+        self.X = to_device(X, device).contiguous()
+        self.n_obs, self.d = self.X.shape
+        self.K = int(K)
+        self.log_pi = (torch.full((self.K,), -float(np.log(self.K)), dtype=torch.float64, device=self.X.device)
+                       if log_pi is None else to_device(log_pi, self.X.device))
+        self.prior_prec = float(prior_prec)
+        self.group = group
+        self.n_global = self.K * self.d
+        self.dim = self.n_global + self.n_obs * (self.K - 1)
+
+    def sparsity_array(self):
+        return self.n_global + np.arange(self.n_obs * (self.K - 1)).reshape(self.n_obs, self.K - 1)
+
+    def _split(self, x):
+        x = to_device(x, self.X.device)
+        return x[:self.n_global].reshape(self.K, self.d), x[self.n_global:].reshape(self.n_obs, self.K - 1)
+
+    def __call__(self, x):
+        m, rho = x[:self.n_global].reshape(self.K, self.d), x[self.n_global:].reshape(self.n_obs, self.K - 1)
+        logits = torch.cat([rho, torch.zeros(self.n_obs, 1, dtype=x.dtype, device=x.device)], dim=1)
+        logr = torch.log_softmax(logits, dim=1)
+        r = torch.exp(logr)
+        c = 0.5 * ((self.X[:, None, :] - m[None, :, :]) ** 2).sum(-1) - self.log_pi[None, :]
+        return torch.sum(r * (c + logr)) + 0.5 * self.prior_prec * torch.sum(m * m)
+
+    def vt_grad(self, x):
+        m, rho = self._split(x)
+        out = ops.gmm_blocks(self.X, m, rho, self.log_pi, want_blocks=False, want_cross=False)
+        r = out['r']
+        # d f / d m_k = sum_n r_nk (m_k - x_n) + prior_prec m_k
+        rsum = r.sum(0)
+        gm = rsum[:, None] * m - ops.gemm(r, self.X, 'KS', 'KS') + self.prior_prec * m
+        return torch.cat([self._allreduce(gm).reshape(-1), out['grad_rho'].reshape(-1)])
+
+    def vt_hessian(self, x):
+        raise NotImplementedError('the dense Hessian of a GMM-VB objective is never formed; use SparseBlockHessian')
+
+    def vt_block_hessian(self, x, sparsity_array, which='full', global_inds=None):
+        from .sparse_hessian_lib import BlockArrowHessian
+        m, rho = self._split(x)
+        want_b = which in ('full', 'block')
+        want_g = which in ('full', 'global')
+        out = ops.gmm_blocks(self.X, m, rho, self.log_pi, want_blocks=want_b, want_cross=want_g)
+        dev = self.X.device
+        gi = torch.arange(self.n_global, dtype=torch.int64, device=dev) if want_g else \
+            torch.empty(0, dtype=torch.int64, device=dev)
+        hgg = None
+        if want_g:
+            rsum = self._allreduce(out['r'].sum(0))
+            hgg = torch.diag((rsum + self.prior_prec).repeat_interleave(self.d))
+        return BlockArrowHessian(self.dim, sparsity_array, gi, blocks=out['blocks'], cross=out['cross'], hgg=hgg)

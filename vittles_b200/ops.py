@@ -285,3 +285,82 @@ def synth_bernoulli(seed, row0, z):
     y = torch.empty_like(z)
     check(lib.vt_synth_bernoulli(ptr(y), ptr(z), int(row0), z.numel(), int(seed), stream()))
     return y
+
+
+# ------------------------------------------------------- block-arrow path ----
+def block_potrf(blocks, check_pd=True):
+    """In-place lower Cholesky of (G, M, M) blocks; returns the same tensor."""
+    lib = _cabi.require_cuda()
+    _f64(blocks, 'blocks')
+    if blocks.dim() != 3 or blocks.shape[1] != blocks.shape[2] or not blocks.is_contiguous():
+        raise ValueError('blocks must be a contiguous (G, M, M) tensor')
+    G, M, _ = blocks.shape
+    info = torch.zeros(1, dtype=torch.int32, device=blocks.device)
+    check(lib.vt_block_potrf_batched(ptr(blocks), G, M, ctypes.c_void_p(info.data_ptr()), stream()))
+    if check_pd:
+        i = int(info.item())
+        if i != 0:
+            raise np.linalg.LinAlgError('block {} of the block-diagonal part is not positive definite'.format(i - 1))
+    return blocks
+
+
+def block_trsm(Lb, C):
+    """C[g] <- L[g]^{-1} C[g] in place, C of shape (G, M, Dg)."""
+    lib = _cabi.require_cuda()
+    G, M, Dg = C.shape
+    if not C.is_contiguous():
+        raise ValueError('C must be contiguous')
+    check(lib.vt_block_trsm_batched(ptr(_f64(Lb, 'Lb')), ptr(_f64(C, 'C')), G, M, Dg, stream()))
+    return C
+
+
+def block_solve(Lb, b, transpose=False):
+    """b[g] <- L[g]^{-1} b[g] (or L[g]^{-T} b[g]) in place, b of shape (G, M)."""
+    lib = _cabi.require_cuda()
+    G, M = b.shape
+    check(lib.vt_block_solve_batched(ptr(_f64(Lb, 'Lb')), ptr(_f64(b, 'b')), G, M, 1 if transpose else 0, stream()))
+    return b
+
+
+def tall_gemv(Z, x, alpha=1.0, y=None, beta=0.0):
+    """y = beta*y + alpha * Z @ x for a (R, Dg) matrix with R very long."""
+    lib = _cabi.require_cuda()
+    _mat(Z, 'Z')
+    R, Dg = Z.shape
+    if y is None:
+        y = torch.empty(R, dtype=torch.float64, device=Z.device)
+        beta = 0.0
+    check(lib.vt_tall_gemv(ptr(Z), R, Dg, ptr(_f64(x, 'x').contiguous()), float(alpha), ptr(y), float(beta), stream()))
+    return y
+
+
+def tall_colsum(Z, u, alpha=1.0, y0=None, beta=1.0):
+    """alpha * Z.T @ u + beta * y0 for a (R, Dg) matrix with R very long."""
+    lib = _cabi.require_cuda()
+    _mat(Z, 'Z')
+    R, Dg = Z.shape
+    out = torch.empty(Dg, dtype=torch.float64, device=Z.device)
+    ws, wsb = _ws('colsum', lib.vt_tall_colsum_workspace_bytes(Dg), Z.device)
+    check(lib.vt_tall_colsum(ptr(Z), R, Dg, ptr(_f64(u, 'u').contiguous()), float(alpha), ptr(y0), float(beta),
+                             ptr(out), ptr(ws), wsb, stream()))
+    return out
+
+
+def gmm_blocks(X, m, rho, log_pi, want_blocks=True, want_cross=True):
+    """Closed-form pieces of the GMM-VB objective: local Hessian blocks
+    (N, K-1, K-1), cross blocks (N, K-1, K*d), responsibilities (N, K), local
+    gradient (N, K-1) and per-observation objective terms (N,)."""
+    lib = _cabi.require_cuda()
+    _mat(X, 'X')
+    N, d = X.shape
+    K = m.shape[0]
+    dev = X.device
+    blocks = torch.empty((N, K - 1, K - 1), dtype=torch.float64, device=dev) if want_blocks else None
+    cross = torch.empty((N, K - 1, K * d), dtype=torch.float64, device=dev) if want_cross else None
+    rmat = torch.empty((N, K), dtype=torch.float64, device=dev)
+    grad_rho = torch.empty((N, K - 1), dtype=torch.float64, device=dev)
+    obj = torch.empty(N, dtype=torch.float64, device=dev)
+    check(lib.vt_gmm_blocks(ptr(X), N, d, K, ptr(_f64(m, 'm').contiguous()), ptr(_f64(rho, 'rho').contiguous()),
+                            ptr(_f64(log_pi, 'log_pi').contiguous()), ptr(blocks), ptr(cross), ptr(rmat),
+                            ptr(grad_rho), ptr(obj), stream()))
+    return dict(blocks=blocks, cross=cross, r=rmat, grad_rho=grad_rho, obj_terms=obj)

@@ -175,5 +175,8 @@ class SparseBlockHessian():
 
     def get_hessian(self, opt_par, print_every=0):
         """Reference ``:165-168``."""
+        if self._structured:
+            x, sa = self._prep(opt_par)
+            return self._fun.vt_block_hessian(x, sa, which='full')
         return self.get_block_hessian(opt_par, print_every=print_every) + \
             self.get_global_hessian(opt_par, print_every=print_every)

@@ -1,0 +1,113 @@
+"""CPU: the C-ABI library loads and exports every symbol the header declares;
+host-side logic that needs no GPU (term bookkeeping, argument validation, the
+fail-loudly rule)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    from vittles_b200 import _cabi
+    header = open(os.path.join(ROOT, 'include', 'vittles_b200.h')).read()
+    declared = set(re.findall(r'\b(vt_[a-z0-9_]+)\s*\(', header))
+    assert len(declared) >= 30
+    lib = _cabi.load()                                   # no GPU needed to load and type the entry points
+    for name in declared:
+        assert hasattr(lib, name), 'library does not export ' + name
+    assert declared == set(_cabi.exported_symbols()), declared ^ set(_cabi.exported_symbols())
+    assert lib.vt_abi_version() == 1
+    assert isinstance(lib.vt_last_error(), bytes)
+    assert lib.vt_potrf_dinv_doubles(1024) == 8 * 128 * 128
+    assert lib.vt_potrf_dinv_doubles(130) == 2 * 128 * 128
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device every compute entry fails loudly."""
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    import vittles_b200 as vt
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        vt.solver_lib.get_cholesky_solver(np.eye(3))
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        vt.objectives.GLMObjective(np.ones((4, 2)), np.ones(4))
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        vt.HyperparameterSensitivityLinearApproximation(lambda t, l: (t * l).sum(), np.ones(2), np.ones(2))
+
+
+def test_product_never_imports_the_oracle():
+    import subprocess, sys
+    code = ("import sys; sys.path.insert(0, %r); import vittles_b200; "
+            "bad=[m for m in sys.modules if m == 'oracle' or m.startswith('oracle.')]; assert not bad, bad" % ROOT)
+    subprocess.check_call([sys.executable, '-c', code])
+    for dirpath, _, files in os.walk(os.path.join(ROOT, 'vittles_b200')):
+        for fn in files:
+            if fn.endswith('.py'):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', src, re.M), fn
+
+
+def test_derivative_terms_host_logic(golden):
+    """tests/test_sensitivity_lib.py:354-401 (differentiate / consolidate)."""
+    from vittles_b200 import sensitivity_lib as sl
+    t = sl.DerivativeTerm(eps_order=1, eta_orders=[1, 0], prefactor=2.0)
+    assert t.order() == 2 and t.total_eta_order == 1
+    kids = t.differentiate()
+    assert len(kids) == 3                                                          # reference :363-381
+    sig = sorted((k.eps_order, tuple(k.eta_orders), k.prefactor) for k in kids)
+    assert sig == [(1, (0, 1, 0), 2.0), (1, (2, 0, 0), 2.0), (2, (1, 0, 0), 2.0)]
+    a = sl.DerivativeTerm(0, [1], 1.0)
+    merged = sl._consolidate_terms([a, sl.DerivativeTerm(0, [1], 2.5), sl.DerivativeTerm(1, [0], 1.0)])
+    assert len(merged) == 2 and merged[0].prefactor == 3.5                         # reference :384-401
+    assert a.check_similarity(sl.DerivativeTerm(0, [1], 9.0))
+    assert str(a).startswith('Order: 1')
+    with pytest.raises(AssertionError):
+        sl.DerivativeTerm(0, [1, 1], 1.0)          # len(eta_orders) must equal the order
+    g = golden('taylor')
+    terms = [sl._get_taylor_base_terms()]
+    for k in range(1, 5):
+        nxt = []
+        for term in terms[-1]:
+            nxt += term.differentiate()
+        terms.append(sl._consolidate_terms(nxt))
+    for k in range(5):
+        ref = {(int(r[1]), tuple(int(x) for x in r[2:2 + k + 1])): r[0] for r in g['table_order{}'.format(k + 1)]}
+        assert {(t.eps_order, tuple(t.eta_orders)): t.prefactor for t in terms[k]} == ref
+
+    # _evaluate_term_fwd expands the directions as the reference does (:720-734)
+    calls = []
+
+    def fake_eval(eta0, eps0, eta_dirs, eps_dirs, validate=False):
+        calls.append((list(eta_dirs), list(eps_dirs)))
+        return 1.0
+    term = sl.DerivativeTerm(eps_order=2, eta_orders=[1, 0, 1, 0, 0, 0], prefactor=3.0)
+    out = sl._evaluate_term_fwd(term, 'e0', 'p0', 'D', ['d1', 'd2', 'd3', 'd4', 'd5'], fake_eval)
+    assert out == 3.0 and calls[0] == (['d1', 'd3'], ['D', 'D'])
+    with pytest.raises(ValueError):
+        sl._evaluate_term_fwd(term, 'e0', 'p0', 'D', ['d1'], fake_eval, validate=True)
+
+
+def test_shard_ranges():
+    from vittles_b200.distributed import shard_range
+    for n, w in [(10_000_000, 8), (1000, 3), (7, 8)]:
+        pieces = [shard_range(n, r, w) for r in range(w)]
+        assert pieces[0][0] == 0 and pieces[-1][1] == n
+        assert all(pieces[i][1] == pieces[i + 1][0] for i in range(w - 1))
+        sizes = [b - a for a, b in pieces]
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(10, 3, 2)
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """`bench.py --impl reference` (the CPU arm) prints one JSON line."""
+    import json, subprocess, sys
+    out = subprocess.check_output([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1',
+                                   '--warmup', '1', '--cpu-sample', '2000', '--dim', '64'], text=True)
+    line = json.loads(out.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['value'] > 0 and line['cpu_baseline']['kind'] == 'port'
+    assert line['e2e']['h2d_bytes_per_step'] == 0

@@ -1,0 +1,155 @@
+"""CPU: the oracle against (a) the golden outputs of the unmodified reference
+(tests/golden/*.npz, made by oracle/make_golden.py) and (b) the closed-form
+truths the reference's own tests assert."""
+import warnings
+
+import numpy as np
+import pytest
+import scipy as sp
+import scipy.sparse
+import torch
+
+from conftest import assert_close
+import oracle
+from oracle import models, fixtures
+
+
+def test_solver_lib_oracle_vs_golden(golden):
+    g = golden('solver_lib')
+    o = oracle.solver_lib
+    h, v, V = g['h'], g['v'], g['V']
+    assert_close(o.get_dense_cholesky_solver(h)(v), g['dense_v'], rtol=1e-12)
+    assert_close(o.get_cholesky_solver(h)(V), g['dense_V'], rtol=1e-12)
+    hs = sp.sparse.csc_matrix(h)
+    assert_close(o.get_cholesky_solver(hs)(v), g['sparse_v'], rtol=1e-12)
+    assert_close(o.get_sparse_cholesky_solver(hs)(V), g['sparse_V'], rtol=1e-12)
+    assert_close(o.get_cg_solver(lambda x: h @ x, 10)(v), g['cg_v'], rtol=1e-12)
+    with pytest.warns(UserWarning):
+        assert_close(o.get_cg_solver(lambda x: hs @ x, 10, {'maxiter': 1})(v), g['cg_maxiter1_v'], rtol=1e-12)
+    with pytest.raises(ValueError):
+        o.get_sparse_cholesky_solver(h)
+    # the reference test's own assertion: everything equals np.linalg.solve to 6 decimals
+    truth = np.linalg.solve(h, v)
+    for k in ('dense_v', 'sparse_v', 'cg_v'):
+        np.testing.assert_array_almost_equal(g[k], truth)
+    x, info, nmv = o.cg_reference_iterates(lambda x: h @ x, v, rtol=1e-5)
+    assert info == 0 and nmv == int(g['cg_v_iters'])
+    assert_close(x, g['cg_v'], rtol=1e-10)
+
+
+@pytest.mark.parametrize('key', ['t0l0', 't0l1', 't1l0', 't1l1'])
+def test_linear_quadratic_oracle_vs_golden(golden, key):
+    g = golden('linear_quadratic')
+    model = fixtures.QuadraticModel(3)
+    tf_, lf = key[1] == '1', key[3] == '1'
+    res = oracle.sensitivity.linear_sensitivity(
+        model.get_flat_objective(tf_, lf), g[key + '_theta0'], g[key + '_lam0'], validate_optimum=True)
+    assert_close(res['sens'], g[key + '_sens'], rtol=1e-12)
+    assert_close(res['hessian'], g[key + '_hess'], rtol=1e-12)
+    np.testing.assert_array_almost_equal(res['sens'], g[key + '_true_jac'])       # reference :551-554
+    pred = oracle.sensitivity.predict_from_hyper(g[key + '_theta0'], g[key + '_lam0'], res['sens'],
+                                                 g[key + '_lam0'] + 0.001)
+    assert_close(pred, g[key + '_pred'], rtol=1e-12)
+    if not tf_ and not lf:
+        # linear in lambda: the prediction is exact (reference :528-531)
+        true1 = model.get_true_optimal_theta(g[key + '_lam0'] + 0.001)
+        np.testing.assert_array_almost_equal(pred, true1)
+
+
+def test_logistic_ij_oracle_vs_golden(golden):
+    g = golden('logistic_ij_cfg1')
+    seed, n, d = int(g['seed']), int(g['n']), int(g['d'])
+    X, y, _ = models.synth_logistic(seed, n, d)
+    assert np.array_equal(X[:4], g['X_head']) and np.array_equal(y[:16], g['y_head'])
+    w = np.ones(n)
+    cf = models.glm_closed_form(X, y, g['theta'], w)
+    assert np.linalg.norm(cf['grad']) < 1e-8
+    assert_close(cf['hessian'], g['hessian'], rtol=1e-11)
+    assert_close(-np.linalg.solve(cf['hessian'], cf['cross_hessian']), g['sens'], rtol=1e-9, atol_scale=1e-12)
+    res = oracle.sensitivity.linear_sensitivity(models.glm_objective(X, y), g['theta'], w)
+    assert_close(res['sens'], g['sens'], rtol=1e-11, atol_scale=1e-13)
+    assert_close(oracle.sensitivity.predict_from_hyper(g['theta'], w, res['sens'], g['w1']), g['pred'], rtol=1e-11)
+    g2 = golden('poisson_ij')
+    cf2 = models.glm_closed_form(g2['X'], g2['y'], g2['theta'], g2['w'], 'poisson', float(g2['l2']))
+    assert_close(-np.linalg.solve(cf2['hessian'], cf2['cross_hessian']), g2['sens'], rtol=1e-9, atol_scale=1e-12)
+
+
+def test_taylor_oracle_vs_golden(golden):
+    g = golden('taylor')
+    tabs = oracle.sensitivity.taylor_term_table(5)
+    for k in range(5):
+        ref = {(int(r[1]), tuple(int(x) for x in r[2:2 + k + 1])): r[0] for r in g['table_order{}'.format(k + 1)]}
+        assert {(e, tuple(o)): p for p, e, o in tabs[k]} == ref
+    # 1, 3, 6, 11 right-hand-side terms for orders 1-4
+    assert [sum(1 for p, e, o in t if o[-1] == 0) for t in tabs[:4]] == [1, 3, 6, 11]
+    model = fixtures.QuadraticModel(3)
+    gq = torch.func.grad(model.get_flat_objective(True, True), argnums=0)
+    solve = oracle.solver_lib.get_cholesky_solver(g['q_hess0'])
+    d = oracle.sensitivity.taylor_input_derivs(gq, g['q_eta0'], g['q_eps0'], g['q_eps1'] - g['q_eps0'], 3, solve)
+    for k in range(3):
+        assert_close(d[k], g['q_derivs'][k], rtol=1e-11, atol_scale=1e-13)
+        np.testing.assert_array_almost_equal(d[k], g['q_true'][k])                 # reference :697-703
+        np.testing.assert_array_almost_equal(g['q_derivs_cg'][k], g['q_true'][k], decimal=4)
+    X, y, _ = models.synth_logistic(int(g['h_seed']), int(g['h_n']), int(g['h_d']))
+    gh = torch.func.grad(models.hier_glm_objective(X, y), argnums=0)
+    dh = oracle.sensitivity.taylor_input_derivs(gh, g['h_theta0'], g['h_eps0'], g['h_eps1'] - g['h_eps0'], 3,
+                                                oracle.solver_lib.get_cholesky_solver(g['h_hess']))
+    for k in range(3):
+        assert_close(dh[k], g['h_derivs'][k], rtol=1e-10, atol_scale=1e-13)
+    # the order-3 series is much closer to the re-optimised optimum than order 1
+    e1 = np.linalg.norm(g['h_theta0'] + g['h_derivs'][0] - g['h_theta1'])
+    e3 = np.linalg.norm(g['h_series'] - g['h_theta1'])
+    assert e3 < 0.2 * e1
+
+
+def test_sparse_hessian_oracle_vs_golden(golden):
+    g = golden('sparse_hessian')
+    f, x, inds, _ = fixtures.block_quadratic(10, 3, with_scales=False)
+    assert_close(oracle.sparse_hessian.block_hessian(f, g['bq_x'], inds).toarray(), g['bq_block_hess'], rtol=1e-12,
+                 atol_scale=1e-14)
+    h0 = torch.func.hessian(f)(torch.as_tensor(g['bq_x'])).numpy()
+    np.testing.assert_array_almost_equal(g['bq_block_hess'], h0)                   # reference :53
+    f2, x2, inds2, ginds2 = fixtures.block_quadratic(10, 3, with_scales=True)
+    assert_close(oracle.sparse_hessian.full_hessian(f2, g['bqs_x'], inds2).toarray(), g['bqs_full_hess'],
+                 rtol=1e-12, atol_scale=1e-14)
+    assert_close(oracle.sparse_hessian.global_hessian(f2, g['bqs_x'], inds2, ginds2).toarray(),
+                 g['bqs_global_hess'], rtol=1e-12, atol_scale=1e-14)
+    with pytest.raises(ValueError):
+        oracle.sparse_hessian.check_sparsity_array(np.array([[0, 1], [1, 2]]))
+    with pytest.raises(ValueError):
+        oracle.sparse_hessian.global_hessian(f2, g['bqs_x'], inds2, np.array([0]))
+    K = int(g['gmm_K'])
+    fg = models.gmm_vb_objective(g['gmm_X'], K)
+    inds = models.gmm_vb_sparsity(g['gmm_X'].shape[0], K, g['gmm_X'].shape[1])
+    assert_close(oracle.sparse_hessian.full_hessian(fg, g['gmm_x'], inds).toarray(), g['gmm_hess'], rtol=1e-11,
+                 atol_scale=1e-13)
+    assert_close(np.linalg.solve(g['gmm_hess'], g['gmm_b']), g['gmm_solve'], rtol=1e-8, atol_scale=1e-10)
+
+
+def test_lr_cov_oracle_vs_golden(golden):
+    g = golden('lr_cov')
+    f = models.mvn_kl_objective(g['true_mean'], g['true_info'])
+    cov = oracle.lr_cov.lr_covariance(f, g['opt'], lambda par: par[:4])
+    assert_close(cov, g['cov'], rtol=1e-11)
+    np.testing.assert_array_almost_equal(g['true_cov'], cov)                      # reference :93
+    opt, H = models.mvn_kl_closed_form(g['true_mean'], g['true_info'])
+    assert_close(H, g['hessian'], rtol=1e-10, atol_scale=1e-13)
+    hess, solve = oracle.lr_cov.base_values(f, g['opt'], validate=True, grad_tol=1e-12)
+    j = oracle.lr_cov.moment_jacobian(lambda par: par[:4], g['opt'])
+    assert_close(oracle.lr_cov.lr_covariance_from_jacobians(solve, 8, j[0:2], j[2:4]), g['cross01_23'], rtol=1e-10,
+                 atol_scale=1e-12)
+    for a, b in [(j.T, j), (j, j.T), (j[:, :, None], j), (j, j[:, :, None])]:
+        with pytest.raises(ValueError):
+            oracle.lr_cov.lr_covariance_from_jacobians(solve, 8, a, b)
+    with pytest.raises(ValueError):
+        oracle.lr_cov.base_values(f, g['opt'] + 0.01, validate=True, grad_tol=1e-12)
+
+
+def test_synth_generator_statistics():
+    X = models.synth_design(1, 0, 4000, 64)
+    assert abs(X.mean()) < 2e-3 and abs(X.var() * 64 - 1.0) < 0.02
+    a = models.synth_design(9, 100, 50, 16)
+    b = models.synth_design(9, 0, 150, 16)[100:]
+    assert np.array_equal(a, b)                      # any row range is reproducible
+    u = models.synth_uniform(3, 0, 10000)
+    assert 0.0 <= u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 0.02

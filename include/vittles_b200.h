@@ -90,6 +90,7 @@ int vt_glm_stats(const double* X, int64_t ldx, int64_t N, int D, const double* t
                  void* workspace, size_t workspace_bytes, void* stream);
 int vt_glm_hvp(const double* X, int64_t ldx, int64_t N, int D, const double* s, const double* v, double ridge,
                double* out, void* workspace, size_t workspace_bytes, void* stream);
+size_t vt_glm_dirderiv_workspace_bytes(int64_t N, int D);
 int vt_glm_dirderiv(const double* X, int64_t ldx, int64_t N, int D, const double* z, const double* w, int family,
                     const double* dirs, int q, double* out, void* workspace, size_t workspace_bytes, void* stream);
 

@@ -150,6 +150,8 @@ int vt_glm_hvp(const double* X, int64_t ldx, int64_t N, int D, const double* s, 
   return glm_hvp(X, ldx, N, D, s, v, ridge, out, static_cast<double*>(workspace), workspace_bytes, S(stream));
 }
 
+size_t vt_glm_dirderiv_workspace_bytes(int64_t N, int D) { return glm_dirderiv_workspace_bytes(N, D); }
+
 int vt_glm_dirderiv(const double* X, int64_t ldx, int64_t N, int D, const double* z, const double* w, int family,
                     const double* dirs, int q, double* out, void* workspace, size_t workspace_bytes, void* stream) {
   return glm_dirderiv(X, ldx, N, D, z, w, family, dirs, q, out, static_cast<double*>(workspace), workspace_bytes,

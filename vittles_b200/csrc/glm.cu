@@ -79,33 +79,43 @@ struct StatsOp {
   const double* y; const double* w;
   double* z; double* resid; double* s;
   int family;
-  __device__ double operator()(long n, const double* t) const {
+  struct Aux { double y, w; };
+  __device__ Aux load(long n) const { return Aux{y[n], w ? w[n] : 1.0}; }
+  __device__ double operator()(long n, const double* t, const Aux& a) const {
     const double zz = t[0];
     double mu, var;
     if (family == GLM_LOGISTIC) { mu = sigmoid(zz); var = mu * (1.0 - mu); }
     else if (family == GLM_POISSON) { mu = exp(zz); var = mu; }
     else { mu = zz; var = 1.0; }
-    const double wn = w ? w[n] : 1.0;
-    const double r = mu - y[n];
+    const double r = mu - a.y;
     if (z) z[n] = zz;
     if (resid) resid[n] = r;
-    if (s) s[n] = wn * var;
-    return wn * r;
+    if (s) s[n] = a.w * var;
+    return a.w * r;
   }
 };
 
 struct HvpOp {
   const double* s;
-  __device__ double operator()(long n, const double* t) const { return s[n] * t[0]; }
+  struct Aux { double s; };
+  __device__ Aux load(long n) const { return Aux{s[n]}; }
+  __device__ double operator()(long n, const double* t, const Aux& a) const { return a.s * t[0]; }
 };
+
+// coef[n] = w_n * b^{(k)}(z_n): elementwise pre-pass of the directional derivative
+__global__ void __launch_bounds__(256) glm_coef_kernel(const double* __restrict__ z, const double* __restrict__ w,
+                                                       long N, int family, int k, const Poly poly, double* coef) {
+  for (long n = (long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (long)gridDim.x * blockDim.x)
+    coef[n] = b_deriv(family, k, z[n], poly) * (w ? w[n] : 1.0);
+}
 
 template <int Q>
 struct DirDerivOp {
-  const double* z; const double* w;
-  int family, k;   // k = Q + 1: derivative order of b
-  Poly poly;
-  __device__ double operator()(long n, const double* t) const {
-    double u = b_deriv(family, k, z[n], poly) * (w ? w[n] : 1.0);
+  const double* coef;
+  struct Aux { double c; };
+  __device__ Aux load(long n) const { return Aux{coef[n]}; }
+  __device__ double operator()(long n, const double* t, const Aux& a) const {
+    double u = a.c;
 #pragma unroll
     for (int j = 0; j < Q; ++j) u *= t[j];
     return u;
@@ -114,12 +124,14 @@ struct DirDerivOp {
 
 template <class RowOp, int Q, int CPT>
 int launch_xtfx(const XtfxParams& p, const RowOp& op, cudaStream_t stream, int* grid_out) {
-  constexpr int R = 16 / CPT;
+  constexpr int R = (CPT <= 8) ? 8 / CPT : 1;
+  constexpr int CTAS_PER_SM = (R * CPT <= 8) ? 2 : 1;
   const size_t smem = xtfx_smem_bytes(p.Dp, R, Q);
-  VT_CUDA(cudaFuncSetAttribute(xtfx_kernel<RowOp, Q, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VT_CUDA(cudaFuncSetAttribute(xtfx_kernel<RowOp, Q, CPT, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long nblocks = (p.N + R - 1) / R;
-  const int grid = (int)(nblocks < num_sms() ? nblocks : num_sms());
-  xtfx_kernel<RowOp, Q, CPT><<<grid, XT_THREADS, smem, stream>>>(p, op);
+  const long cap = (long)num_sms() * CTAS_PER_SM;
+  const int grid = (int)(nblocks < cap ? nblocks : cap);
+  xtfx_kernel<RowOp, Q, CPT, R><<<grid, XT_THREADS, smem, stream>>>(p, op);
   VT_LAUNCH_CHECK();
   *grid_out = grid;
   return VT_OK;
@@ -158,7 +170,7 @@ int make_params(XtfxParams& p, const double* X, long ldx, long N, int D, const d
 
 }  // namespace
 
-size_t glm_workspace_bytes(int D) { return (size_t)num_sms() * ((D + 1) & ~1) * 8; }
+size_t glm_workspace_bytes(int D) { return (size_t)num_sms() * 2 * ((D + 1) & ~1) * 8; }
 
 int glm_stats(const double* X, long ldx, long N, int D, const double* theta, const double* y, const double* w,
               int family, double* z, double* resid, double* s, double* grad, double l2, double* workspace,
@@ -194,22 +206,32 @@ int glm_hvp(const double* X, long ldx, long N, int D, const double* s, const dou
   return VT_OK;
 }
 
+size_t glm_dirderiv_workspace_bytes(long N, int D) { return glm_workspace_bytes(D) + (size_t)N * 8; }
+
 int glm_dirderiv(const double* X, long ldx, long N, int D, const double* z, const double* w, int family,
                  const double* dirs, int q, double* out, double* workspace, size_t workspace_bytes,
                  cudaStream_t stream) {
   VT_REQUIRE(z && out, "glm_dirderiv: null pointer");
   VT_REQUIRE(q >= 1 && q <= XT_MAXQ, "glm_dirderiv: number of directions must be 1..%d, got %d", XT_MAXQ, q);
   VT_REQUIRE(q + 1 <= GLM_MAX_BDERIV, "glm_dirderiv: derivative order too high");
+  VT_REQUIRE(family >= 0 && family <= 2, "glm_dirderiv: unknown family %d", family);
+  VT_REQUIRE(workspace && workspace_bytes >= glm_dirderiv_workspace_bytes(N, D),
+             "glm_dirderiv: workspace too small: need %zu bytes", glm_dirderiv_workspace_bytes(N, D));
   XtfxParams p;
   int st = make_params(p, X, ldx, N, D, dirs, workspace, workspace_bytes, true);
   if (st != VT_OK) return st;
-  int grid = 0;
+  double* coef = workspace + glm_workspace_bytes(D) / 8;
   const Poly poly = logistic_poly(q + 1);
+  const long want = (N + 255) / 256;
+  const int cgrid = (int)(want < (long)num_sms() * 8 ? want : (long)num_sms() * 8);
+  glm_coef_kernel<<<cgrid, 256, 0, stream>>>(z, w, N, family, q + 1, poly, coef);
+  VT_LAUNCH_CHECK();
+  int grid = 0;
   switch (q) {
-    case 1: { DirDerivOp<1> op{z, w, family, 2, poly}; st = dispatch_cpt<DirDerivOp<1>, 1>(p, op, stream, &grid); break; }
-    case 2: { DirDerivOp<2> op{z, w, family, 3, poly}; st = dispatch_cpt<DirDerivOp<2>, 2>(p, op, stream, &grid); break; }
-    case 3: { DirDerivOp<3> op{z, w, family, 4, poly}; st = dispatch_cpt<DirDerivOp<3>, 3>(p, op, stream, &grid); break; }
-    default: { DirDerivOp<4> op{z, w, family, 5, poly}; st = dispatch_cpt<DirDerivOp<4>, 4>(p, op, stream, &grid); break; }
+    case 1: { DirDerivOp<1> op{coef}; st = dispatch_cpt<DirDerivOp<1>, 1>(p, op, stream, &grid); break; }
+    case 2: { DirDerivOp<2> op{coef}; st = dispatch_cpt<DirDerivOp<2>, 2>(p, op, stream, &grid); break; }
+    case 3: { DirDerivOp<3> op{coef}; st = dispatch_cpt<DirDerivOp<3>, 3>(p, op, stream, &grid); break; }
+    default: { DirDerivOp<4> op{coef}; st = dispatch_cpt<DirDerivOp<4>, 4>(p, op, stream, &grid); break; }
   }
   if (st != VT_OK) return st;
   xtfx_reduce_kernel<<<(D + 255) / 256, 256, 0, stream>>>(p.partial, grid, p.Dp, D, out, 1.0, nullptr, 0.0);

@@ -20,6 +20,7 @@ int glm_hvp(const double* X, long ldx, long N, int D, const double* s, const dou
             double* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 // out = X^T ( w .* b^{(q+1)}(z) .* prod_j (X dirs_j) ),  dirs is (q, D) row-major
+size_t glm_dirderiv_workspace_bytes(long N, int D);
 int glm_dirderiv(const double* X, long ldx, long N, int D, const double* z, const double* w, int family,
                  const double* dirs, int q, double* out, double* workspace, size_t workspace_bytes,
                  cudaStream_t stream);

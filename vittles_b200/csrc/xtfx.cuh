@@ -6,11 +6,11 @@
 //   * Hessian-vector product         (Q=1; u = s_n * t)            -> CG solver
 //   * Taylor directional derivatives (Q=m; u = c_n * prod_j t_j)   -> dirderiv
 //
-// Structure (B200): persistent CTAs, one per SM, 256 threads.  A block of
-// R = 16/CPT rows (64 KB for D = 512*CPT) is staged in shared memory by ONE
+// Structure (B200): persistent CTAs, two per SM, 256 threads.  A block of
+// R = 8/CPT rows (32 KB for D = 512*CPT) is staged in shared memory by ONE
 // bulk-TMA copy (cp.async.bulk ... mbarrier::complete_tx; SASS UBLKCP) into a
-// 3-deep ring, so up to 192 KB per SM are in flight with a single issuing
-// thread.  Thread t owns columns {2t, 2t+1} + 512*i: it pulls its 16 double2
+// 3-deep ring, so up to 192 KB per SM are in flight with one issuing thread per
+// CTA.  Thread t owns columns {2t, 2t+1} + 512*i: it pulls its 16 double2
 // of the block into registers once, uses them for the partial dot products
 // (warp-shuffle reduction, then an 8-way cross-warp sum) and again for the
 // rank-R update of its private column accumulators.  Per-CTA column sums go to a
@@ -70,9 +70,12 @@ inline size_t xtfx_smem_bytes(int Dp, int R, int Q) {
   return (size_t)XT_NBUF * R * Dp * 8 + (size_t)(8 * R * Q + R) * 8 + XT_NBUF * 8 + 128;
 }
 
-template <class RowOp, int Q, int CPT>
-__global__ void __launch_bounds__(XT_THREADS, 1) xtfx_kernel(const XtfxParams p, const RowOp op) {
-  constexpr int R = 16 / CPT;
+// R rows per block, CPT double2 columns per thread: R*CPT = 8 gives 32 KB blocks at
+// D = 512*CPT, a 96 KB ring and two CTAs per SM, so that the block-wide syncs and
+// the serial row-functor step of one CTA overlap the other's arithmetic (one
+// CTA per SM left stats at 62% and the HVP at 79% of HBM peak, profiles/r01).
+template <class RowOp, int Q, int CPT, int R>
+__global__ void __launch_bounds__(XT_THREADS, (R * CPT <= 8) ? 2 : 1) xtfx_kernel(const XtfxParams p, const RowOp op) {
   extern __shared__ __align__(128) unsigned char xt_raw[];
   const int Dp = p.Dp;
   double* bufs = reinterpret_cast<double*>(xt_raw);
@@ -142,6 +145,11 @@ __global__ void __launch_bounds__(XT_THREADS, 1) xtfx_kernel(const XtfxParams p,
       }
       __syncthreads();
     }
+    // per-row operands of the row functor (y, w, z, s ...): issue the global loads
+    // now so that their latency overlaps the dot products instead of sitting in
+    // the serial functor step
+    typename RowOp::Aux aux;
+    if (tid < R && tid < rows) aux = op.load(row0 + tid);
     double2 x[R][CPT];
 #pragma unroll
     for (int r = 0; r < R; ++r)
@@ -178,7 +186,7 @@ __global__ void __launch_bounds__(XT_THREADS, 1) xtfx_kernel(const XtfxParams p,
         for (int w = 0; w < 8; ++w) s += s_part[(w * R + tid) * Q + j];
         t[j] = s;
       }
-      s_u[tid] = (tid < rows) ? op(row0 + tid, t) : 0.0;
+      s_u[tid] = (tid < rows) ? op(row0 + tid, t, aux) : 0.0;
     }
     if (p.partial) {
       __syncthreads();

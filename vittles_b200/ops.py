@@ -159,7 +159,7 @@ def glm_dirderiv(X, z, dirs, w=None, family='logistic', out=None):
         raise ValueError('dirs must have shape (q, D)')
     if out is None:
         out = torch.empty(D, dtype=torch.float64, device=X.device)
-    ws, wsb = _ws('glm', lib.vt_glm_workspace_bytes(D), X.device)
+    ws, wsb = _ws('glm', lib.vt_glm_dirderiv_workspace_bytes(N, D), X.device)
     check(lib.vt_glm_dirderiv(ptr(X), _ld(X), N, D, ptr(_f64(z, 'z')), ptr(w), _cabi.GLM_FAMILIES[family],
                               ptr(dirs), dirs.shape[0], ptr(out), ptr(ws), wsb, stream()))
     return out

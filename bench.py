@@ -286,7 +286,8 @@ def main():
     traffic = None
     try:
         with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
-            traffic = json.load(f).get('ij_apply_dram_bytes_per_launch')
+            traffic = json.load(f).get('ij_apply_dram_bytes_per_obs')
+            traffic = None if traffic is None else traffic * n_loc      # per launch at this run's shard size
     except Exception:
         pass
 
@@ -332,6 +333,8 @@ def main():
                                         'MEASURED_PEAKS.json has no FP64 entry; tools/fp64_peak.cu gave '
                                         '{} TFLOP/s'.format(FP64_PEAK_FALLBACK_TFLOPS),
                          'traffic': traffic,
+                         'traffic_source': 'profiles/ncu_traffic.json: dram__bytes_read+write of one ncu --set full '
+                                           'launch at N=1e6, scaled per observation; algorithmic = 16*D bytes/obs',
                          'algorithmic': '2*D^2 flop per observation'},
             'kernels': {
                 'ij_apply': {'ms': t_apply, 'tflops': apply_tflops, 'frac_fp64_peak': apply_tflops / peak_tflops},
@@ -377,15 +380,13 @@ def run_e2e(args, vt, torch, dist, dev, group, world, host):
     d2h = (D + D * D) * 8
 
     def step():
-        Xd = X_host.to(dev, non_blocking=True)
-        yd = y_host.to(dev, non_blocking=True)
-        wd = w_host.to(dev, non_blocking=True)
-        w1d = w1_host.to(dev, non_blocking=True)
-        td = theta_host.to(dev, non_blocking=True)
-        o = vt.objectives.GLMObjective(Xd, yd, family='logistic', group=group)
-        sens = vt.HyperparameterSensitivityLinearApproximation(o, td, wd)
-        pred = sens.predict_opt_par_from_hyper_par(w1d).cpu()
-        hess = sens.get_hessian_at_opt().cpu()
+        # host (pinned) buffers straight into the public API: GLMObjective starts chunked
+        # asynchronous copies and the statistics + Hessian sweep runs behind them
+        o = vt.objectives.GLMObjective(X_host, y_host, family='logistic', group=group)
+        sens = vt.HyperparameterSensitivityLinearApproximation(o, theta_host, w_host)
+        pred = sens.predict_opt_par_from_hyper_par(w1_host)      # D doubles, returned on the host
+        hess = sens.get_hessian_at_opt()                         # D x D, returned on the host
+        assert not pred.is_cuda and not hess.is_cuda
         return pred, hess
 
     def barrier():

@@ -53,8 +53,13 @@ class GLMObjective(StructuredObjective):
 
     ``family``: 'logistic' (b = softplus), 'poisson' (b = exp), 'gaussian'."""
 
-    def __init__(self, X, y, family='logistic', l2=0.0, device=None, group=None):
-        self.X = to_device(X, device)
+    def __init__(self, X, y, family='logistic', l2=0.0, device=None, group=None, stream_chunks=16):
+        self._pending, self._host_src = [], None
+        if (isinstance(X, torch.Tensor) and not X.is_cuda and X.dim() == 2 and X.dtype == torch.float64
+                and X.is_contiguous() and X.is_pinned() and X.shape[0] >= 64 * stream_chunks):
+            self.X = self._stream_from_host(X, device, stream_chunks)
+        else:
+            self.X = to_device(X, device)
         if self.X.dim() != 2:
             raise ValueError('X must be (N, D)')
         self.X = self.X if self.X.stride(1) == 1 else self.X.contiguous()
@@ -68,8 +73,79 @@ class GLMObjective(StructuredObjective):
         self.group = group
         self.n_obs, self.dim = self.X.shape
 
+    # -- host -> device streaming -----------------------------------------------
+    def _stream_from_host(self, X_host, device, nchunks):
+        """Pinned host design matrix: allocate the device copy now, transfer it in
+        chunks on a side stream when the first sweep starts, with one event per
+        chunk, so that the statistics pass and the Hessian assembly of chunk i
+        overlap the transfer of chunk i+1 (the 82 GB transfer, not the arithmetic,
+        bounds the end-to-end time).  The copies are NOT issued here: the H2D copy
+        engine is FIFO, and small blocking copies issued later (y, theta, w) would
+        wait behind the whole design matrix."""
+        from ._arrays import default_device
+        dev = default_device() if device is None else torch.device(device)
+        self._host_src, self._nchunks = X_host, nchunks
+        return torch.empty(X_host.shape, dtype=torch.float64, device=dev)
+
+    def _start_copies(self):
+        if self._host_src is None:
+            return
+        X_host, nchunks, Xd = self._host_src, self._nchunks, self.X
+        self._host_src = None
+        n = X_host.shape[0]
+        copy_stream = torch.cuda.Stream(device=Xd.device)
+        copy_stream.wait_stream(torch.cuda.current_stream(Xd.device))
+        Xd.record_stream(copy_stream)
+        with torch.cuda.stream(copy_stream):
+            for c in range(nchunks):
+                r0, r1 = (n * c) // nchunks, (n * (c + 1)) // nchunks
+                Xd[r0:r1].copy_(X_host[r0:r1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                self._pending.append((r0, r1, ev))
+
+    def _wait_resident(self):
+        """Make the current stream wait for the whole of X (no-op once resident)."""
+        self._start_copies()
+        if self._pending:
+            torch.cuda.current_stream(self.X.device).wait_event(self._pending[-1][2])
+            self._pending = []
+
+    def vt_stats_and_hessian(self, theta, w):
+        """(stats, H) in one sweep.  While a host transfer is in flight the sweep
+        runs chunk by chunk behind the copies; otherwise it is vt_stats + vt_hessian."""
+        if self._host_src is None and not self._pending:
+            stats = self.vt_stats(theta, w)
+            return stats, self.vt_hessian(theta, w, stats)
+        dev = self.X.device
+        theta = to_device(theta, dev)
+        w = None if w is None else to_device(w, dev).contiguous()
+        self._start_copies()          # after the small operands: the copy engine is FIFO
+        n, d = self.X.shape
+        z = torch.empty(n, dtype=torch.float64, device=dev)
+        resid, s = torch.empty_like(z), torch.empty_like(z)
+        grad = torch.zeros(d, dtype=torch.float64, device=dev)
+        H = torch.zeros((d, d), dtype=torch.float64, device=dev)
+        Hc = torch.empty_like(H)
+        cur = torch.cuda.current_stream(dev)
+        pending, self._pending = self._pending, []
+        for r0, r1, ev in pending:
+            cur.wait_event(ev)
+            _, _, _, g = ops.glm_stats(self.X[r0:r1], theta, self.y[r0:r1], None if w is None else w[r0:r1],
+                                       self.family, want_grad=True, out=(z[r0:r1], resid[r0:r1], s[r0:r1]))
+            grad += g
+            ops.syrk_weighted(self.X[r0:r1], s[r0:r1], out=Hc)
+            H += Hc
+        self._allreduce(grad)
+        self._allreduce(H)
+        if self.l2 != 0.0:
+            grad = grad + self.l2 * theta
+            H.diagonal().add_(self.l2)
+        return dict(z=z, resid=resid, s=s, grad=grad), H
+
     # -- generic torch objective (small problems, autodiff checks) ----------
     def __call__(self, theta, w):
+        self._wait_resident()
         z = self.X @ theta
         val = torch.sum(w * (_b(z, self.family) - self.y * z))
         if self.group is not None and dist.is_initialized():
@@ -79,6 +155,7 @@ class GLMObjective(StructuredObjective):
     # -- kernel hooks ---------------------------------------------------------
     def vt_stats(self, theta, w=None, want_grad=True):
         """z, resid = b'(z) - y, s = w b''(z) and the (all-reduced) gradient."""
+        self._wait_resident()
         theta = to_device(theta, self.X.device)
         w = None if w is None else to_device(w, self.X.device).contiguous()
         z, resid, s, grad = ops.glm_stats(self.X, theta, self.y, w, self.family, l2=0.0, want_grad=want_grad)
@@ -95,6 +172,7 @@ class GLMObjective(StructuredObjective):
         """H = X^T diag(w b''(z)) X + l2 I, all-reduced over the group."""
         if stats is None:
             stats = self.vt_stats(theta, w, want_grad=False)
+        self._wait_resident()
         H = ops.syrk_weighted(self.X, stats['s'], l2=0.0)
         self._allreduce(H)
         if self.l2 != 0.0:
@@ -103,6 +181,7 @@ class GLMObjective(StructuredObjective):
 
     def vt_ij_sensitivity(self, hinv, stats, out=None):
         """-H^{-1} G^T for this rank's observations, (D, N_local)."""
+        self._wait_resident()
         return ops.ij_apply(hinv, self.X, stats['resid'], out=out)
 
     def vt_hvp_fn(self, theta, w):
@@ -120,6 +199,7 @@ class GLMObjective(StructuredObjective):
     def vt_directional_derivative(self, theta, w, eta_dirs, eps_dirs, cache=None):
         """d^{m+n} g / d theta^m d w^n contracted with the directions, where
         g = grad_theta f.  g is linear in w, so n >= 2 gives zero."""
+        self._wait_resident()
         dev = self.X.device
         theta = to_device(theta, dev)
         m, n = len(eta_dirs), len(eps_dirs)

@@ -118,16 +118,20 @@ def syrk_weighted(X, s=None, l2=0.0, out=None):
 
 
 # ------------------------------------------------------------- GLM passes ----
-def glm_stats(X, theta, y, w=None, family='logistic', l2=0.0, want_grad=True, want_z=True):
+def glm_stats(X, theta, y, w=None, family='logistic', l2=0.0, want_grad=True, want_z=True, out=None):
     """One pass over X: z = X theta, resid = b'(z) - y, s = w b''(z) and
-    (optionally) grad = X^T (w resid) + l2 theta."""
+    (optionally) grad = X^T (w resid) + l2 theta.  ``out=(z, resid, s)`` writes the
+    per-observation outputs into existing (slices of) tensors."""
     lib = _cabi.require_cuda()
     _mat(X, 'X')
     N, D = X.shape
     dev = X.device
-    z = torch.empty(N, dtype=torch.float64, device=dev) if want_z else None
-    resid = torch.empty(N, dtype=torch.float64, device=dev)
-    s = torch.empty(N, dtype=torch.float64, device=dev)
+    if out is not None:
+        z, resid, s = out
+    else:
+        z = torch.empty(N, dtype=torch.float64, device=dev) if want_z else None
+        resid = torch.empty(N, dtype=torch.float64, device=dev)
+        s = torch.empty(N, dtype=torch.float64, device=dev)
     grad = torch.empty(D, dtype=torch.float64, device=dev) if want_grad else None
     ws, wsb = _ws('glm', lib.vt_glm_workspace_bytes(D), dev)
     check(lib.vt_glm_stats(ptr(X), _ld(X), N, D, ptr(_f64(theta, 'theta').contiguous()), ptr(_f64(y, 'y')),

@@ -217,7 +217,9 @@ class HyperparameterSensitivityLinearApproximation(EstimatingEquationLinearAppro
         if hessian_at_opt is None:
             theta = to_device(opt_par_value).reshape(-1)
             lam = to_device(hyper_par_value, theta.device).reshape(-1)
-            if self._structured:
+            if self._structured and hasattr(self._objective_fun, 'vt_stats_and_hessian'):
+                self._stats, self._hess0 = self._objective_fun.vt_stats_and_hessian(theta, lam)
+            elif self._structured:
                 self._stats = self._objective_fun.vt_stats(theta, lam)
                 self._hess0 = self._objective_fun.vt_hessian(theta, lam, self._stats)
             else:

@@ -5,8 +5,8 @@
 //
 // produced by SparseBlockHessian (reference: sparse_hessian_lib.py:69-168) and
 // solved upstream by SuperLU (solver_lib.py:46-48).  Here:
-//   block_potrf : L_g = chol(B_g)                  one warp per block, shared memory
-//   block_trsm  : Z_g = L_g^{-1} C_g  (in place)   one CTA per block, thread = column
+//   block_potrf : L_g = chol(B_g)                  one warp per block, rows in registers
+//   block_trsm  : Z_g = L_g^{-1} C_g  (in place)   thread = (block, column), L_g in shared memory
 //   block_solve : y_g = L_g^{-1} b_g / L_g^{-T} b_g
 //   tall_gemv   : y = beta*y + alpha * Z x         Z (R x Dg), R ~ G*M huge, Dg short
 //   tall_colsum : out = Z^T u                      deterministic two-stage reduction
@@ -26,9 +26,13 @@ namespace {
 constexpr int MAXM = BLOCK_MAXM;   // 32
 
 // ---------------------------------------------------------------- potrf ----
-// 4 warps per CTA, one block per warp at a time; lane i owns row i.
+// 4 warps per CTA, one block per warp at a time.  The block is staged through
+// shared memory (coalesced global traffic); lane i then owns row i in registers,
+// the pivot column is broadcast with shuffles, and every pivot costs one rsqrt
+// and no division (the serial chain of a 19 x 19 block is ~19 x 150 clocks).
+template <int MT>
 __global__ void __launch_bounds__(128) block_potrf_kernel(double* blocks, long G, int M, int* info) {
-  __shared__ double sm[4][MAXM * (MAXM + 1)];
+  __shared__ double sm[4][MT * (MT + 1)];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* a = sm[warp];
   const int ld = M + 1;
@@ -36,54 +40,79 @@ __global__ void __launch_bounds__(128) block_potrf_kernel(double* blocks, long G
     double* B = blocks + g * M * M;
     for (int e = lane; e < M * M; e += 32) a[(e / M) * ld + (e % M)] = B[e];
     __syncwarp();
+    double r[MT];
+#pragma unroll
+    for (int k = 0; k < MT; ++k) r[k] = (lane < M && k <= lane) ? a[lane * ld + k] : 0.0;
     bool bad = false;
-    for (int j = 0; j < M; ++j) {
-      double d = a[j * ld + j];
-      if (!(d > 0.0)) { bad = true; d = 1.0; }
-      const double s = sqrt(d);
-      double l = 0.0;
-      if (lane > j && lane < M) { l = a[lane * ld + j] / s; a[lane * ld + j] = l; }
-      if (lane == j) a[j * ld + j] = s;
-      __syncwarp();
-      if (lane > j && lane < M) {
-        for (int k = j + 1; k <= lane; ++k) a[lane * ld + k] = fma(-l, a[k * ld + j], a[lane * ld + k]);
+#pragma unroll
+    for (int j = 0; j < MT; ++j) {
+      if (j < M) {
+        double d = __shfl_sync(0xffffffffu, r[j], j);
+        if (!(d > 0.0)) { bad = true; d = 1.0; }
+        const double rs = rsqrt(d);
+        const double l = (lane > j) ? r[j] * rs : (lane == j ? d * rs : 0.0);
+        r[j] = l;
+#pragma unroll
+        for (int k = j + 1; k < MT; ++k) {
+          const double lk = __shfl_sync(0xffffffffu, l, k);
+          r[k] = fma(-l, lk, r[k]);
+        }
       }
-      __syncwarp();
     }
     if (bad && lane == 0) atomicCAS(info, 0, (int)(g < 2147483647L ? g + 1 : 2147483647L));
-    for (int e = lane; e < M * M; e += 32) {
-      const int i = e / M, k = e % M;
-      B[e] = (k <= i) ? a[i * ld + k] : 0.0;
-    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < MT; ++k)
+      if (lane < M && k < M) a[lane * ld + k] = (k <= lane) ? r[k] : 0.0;
+    __syncwarp();
+    for (int e = lane; e < M * M; e += 32) B[e] = a[(e / M) * ld + (e % M)];
     __syncwarp();
   }
 }
 
 // ----------------------------------------------------------------- trsm ----
-// Z = L^{-1} C for one block per CTA iteration; thread t owns columns t, t+256, ...
-__global__ void __launch_bounds__(256) block_trsm_kernel(const double* __restrict__ Lb, double* C, long G, int M,
-                                                         int Dg) {
-  __shared__ double sl[MAXM * MAXM];
-  __shared__ double sinv[MAXM];
-  for (long g = blockIdx.x; g < G; g += gridDim.x) {
+// Z = L^{-1} C in place.  A CTA takes TRSM_BPC consecutive blocks at a time;
+// work items are (block, column) pairs flattened over the threads, so that the
+// global accesses of a warp are contiguous along the column index and every
+// thread has all M loads of its column in flight before the substitution
+// starts (HBM bound: 16 M Dg bytes per block).
+constexpr int TRSM_BPC = 4;
+template <int MT>
+__global__ void __launch_bounds__(256) block_trsm_kernel(const double* __restrict__ Lb, double* __restrict__ C, long G,
+                                                         int M, int Dg) {
+  __shared__ double sl[TRSM_BPC][MT * MT];
+  __shared__ double sinv[TRSM_BPC][MT];
+  const int MM = M * M;
+  for (long g0 = (long)blockIdx.x * TRSM_BPC; g0 < G; g0 += (long)gridDim.x * TRSM_BPC) {
+    const int nb = (int)(G - g0 < TRSM_BPC ? G - g0 : TRSM_BPC);
     __syncthreads();
-    for (int e = threadIdx.x; e < M * M; e += blockDim.x) sl[e] = Lb[g * M * M + e];
+    for (int e = threadIdx.x; e < nb * MM; e += blockDim.x) sl[e / MM][e % MM] = Lb[g0 * MM + e];
     __syncthreads();
-    if (threadIdx.x < M) sinv[threadIdx.x] = 1.0 / sl[threadIdx.x * M + threadIdx.x];
+    if (threadIdx.x < nb * M) {
+      const int b = threadIdx.x / M, i = threadIdx.x % M;
+      sinv[b][i] = 1.0 / sl[b][i * M + i];
+    }
     __syncthreads();
-    double* Cg = C + g * (long)M * Dg;
-    for (int c = threadIdx.x; c < Dg; c += blockDim.x) {
-      double z[MAXM];
+    for (int item = threadIdx.x; item < nb * Dg; item += blockDim.x) {
+      const int b = item / Dg, c = item - b * Dg;
+      double* Cg = C + (g0 + b) * (long)M * Dg + c;
+      const double* L = sl[b];
+      double z[MT];
 #pragma unroll
-      for (int i = 0; i < MAXM; ++i) {
+      for (int i = 0; i < MT; ++i)
+        if (i < M) z[i] = Cg[(long)i * Dg];
+#pragma unroll
+      for (int i = 0; i < MT; ++i) {
         if (i < M) {
-          double s = Cg[(long)i * Dg + c];
+          double s = z[i];
 #pragma unroll
-          for (int k = 0; k < i; ++k) s = fma(-sl[i * M + k], z[k], s);
-          z[i] = s * sinv[i];
-          Cg[(long)i * Dg + c] = z[i];
+          for (int k = 0; k < i; ++k) s = fma(-L[i * M + k], z[k], s);
+          z[i] = s * sinv[b][i];
         }
       }
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+        if (i < M) Cg[(long)i * Dg] = z[i];
     }
   }
 }
@@ -220,12 +249,14 @@ __global__ void __launch_bounds__(256) gmm_blocks_kernel(const double* __restric
       }
     }
     if (cross) {
+      // thread = global column c = (k, t); one coalesced row of C_n per j
       const int Dg = K * d;
       double* Cn = cross + n * (long)M * Dg;
-      for (int e = threadIdx.x; e < M * Dg; e += blockDim.x) {
-        const int j = e / Dg, c = e % Dg;
-        const int k = c / d, t = c % d;
-        Cn[e] = sr[j] * ((j == k ? 1.0 : 0.0) - sr[k]) * (m[(long)k * d + t] - sx[t]);
+      for (int c = threadIdx.x; c < Dg; c += blockDim.x) {
+        const int k = c / d, t = c - k * d;
+        const double dm = m[(long)k * d + t] - sx[t];
+        const double rk = sr[k];
+        for (int j = 0; j < M; ++j) Cn[(long)j * Dg + c] = sr[j] * ((j == k ? 1.0 : 0.0) - rk) * dm;
       }
     }
   }
@@ -243,14 +274,22 @@ int grid_for(long work, int per_cta, int max_ctas_per_sm) {
 int block_potrf(double* blocks, long G, int M, int* info, cudaStream_t stream) {
   VT_REQUIRE(blocks && info && G >= 1 && M >= 1 && M <= MAXM, "block_potrf: need 1 <= M <= %d", MAXM);
   VT_CUDA(cudaMemsetAsync(info, 0, sizeof(int), stream));
-  block_potrf_kernel<<<grid_for(G, 4, 6), 128, 0, stream>>>(blocks, G, M, info);
+  const int grid = grid_for(G, 4, 4);
+  if (M <= 8) block_potrf_kernel<8><<<grid, 128, 0, stream>>>(blocks, G, M, info);
+  else if (M <= 16) block_potrf_kernel<16><<<grid, 128, 0, stream>>>(blocks, G, M, info);
+  else if (M <= 24) block_potrf_kernel<24><<<grid, 128, 0, stream>>>(blocks, G, M, info);
+  else block_potrf_kernel<32><<<grid, 128, 0, stream>>>(blocks, G, M, info);
   VT_LAUNCH_CHECK();
   return VT_OK;
 }
 
 int block_trsm(const double* Lb, double* C, long G, int M, int Dg, cudaStream_t stream) {
   VT_REQUIRE(Lb && C && G >= 1 && M >= 1 && M <= MAXM && Dg >= 1, "block_trsm: bad arguments");
-  block_trsm_kernel<<<grid_for(G, 1, 8), 256, 0, stream>>>(Lb, C, G, M, Dg);
+  const int grid = grid_for(G, TRSM_BPC, 3);
+  if (M <= 8) block_trsm_kernel<8><<<grid, 256, 0, stream>>>(Lb, C, G, M, Dg);
+  else if (M <= 16) block_trsm_kernel<16><<<grid, 256, 0, stream>>>(Lb, C, G, M, Dg);
+  else if (M <= 24) block_trsm_kernel<24><<<grid, 256, 0, stream>>>(Lb, C, G, M, Dg);
+  else block_trsm_kernel<32><<<grid, 256, 0, stream>>>(Lb, C, G, M, Dg);
   VT_LAUNCH_CHECK();
   return VT_OK;
 }

@@ -24,45 +24,55 @@ __device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int& 
   }
 }
 
+template <int TM>
 __device__ __forceinline__ Unit decode_unit(const GemmParams& p, long u) {
   Unit r;
   const int tile = (int)(u % p.ntiles);
   const int part = (int)(u / p.ntiles);
   int tm, tn;
   tile_coords(p, tile, tm, tn);
-  r.m0 = tm * BM;
-  r.n0 = tn * BN;
+  r.m0 = tm * TM;
+  r.n0 = tn * TM;
   const int q = p.kiters / p.parts, rem = p.kiters % p.parts;
   r.kit0 = part * q + min(part, rem);
   r.nkit = q + (part < rem ? 1 : 0);
   return r;
 }
 
-// Kernel configuration: warp grid over the 128x128 CTA tile and whether the
-// DMMA fragments are double buffered in registers.
-template <int WARPS_M_, int WARPS_N_, bool DBUF_>
+// Kernel configuration: square CTA tile TM x TM (128: the throughput
+// configuration; 64: twice the CTAs per SM and a quarter of the work per tile,
+// for short-K / few-tile problems such as the Cholesky panels and for outputs
+// that 128-wide tiles cover wastefully), the warp grid over it, whether the DMMA
+// fragments are double buffered in registers, and the CTAs resident per SM.
+template <int TM_, int WARPS_M_, int WARPS_N_, bool DBUF_, int CTAS_PER_SM_>
 struct GemmCfg {
+  static constexpr int TM = TM_;
   static constexpr int WARPS_M = WARPS_M_, WARPS_N = WARPS_N_;
   static constexpr int NTHREADS = WARPS_M_ * WARPS_N_ * 32;
-  static constexpr int MT = BM / (WARPS_M_ * 8), NT = BN / (WARPS_N_ * 8);
-  static constexpr int VC = (BM * BK / 2) / NTHREADS;   // 16-byte chunks per operand per thread per stage
+  static constexpr int MT = TM_ / (WARPS_M_ * 8), NT = TM_ / (WARPS_N_ * 8);
+  static constexpr int VC = (TM_ * BK / 2) / NTHREADS;   // 16-byte chunks per operand per thread per stage
   static constexpr bool DBUF = DBUF_;
+  static constexpr int CTAS_PER_SM = CTAS_PER_SM_;
+  static constexpr int LDKS = TM_ + 4;                   // = 4 (mod 16) for TM = 64, 128
+  static constexpr int TILE_DOUBLES = TM_ * LDKC;        // >= BK * LDKS
+  static constexpr int SMEM_BYTES = (2 * STAGES * TILE_DOUBLES + STAGES * BK) * 8;
 };
 
 // Copy one 16-byte chunk (VEC) or two 8-byte elements (!VEC: odd leading
-// dimension or unaligned base) of an operand tile (128 rows x 16 k) into shared
+// dimension or unaligned base) of an operand tile (TM rows x 16 k) into shared
 // memory; `chunk` in [0, VC).  Straight-line and fully predicated (zero fill
 // outside the matrix or when `live` is false) so that ptxas can interleave the
 // copies with the DMMA stream: a runtime branch per chunk splits the hot loop
 // into dozens of basic blocks and costs ~20% of the tensor pipe (r01 tuning).
-template <int MODE, bool VEC, int NTHREADS>
+template <int MODE, bool VEC, int NTHREADS, int TM>
 __device__ __forceinline__ void issue_chunk(double* __restrict__ s, const double* __restrict__ gp, long ld, int r0,
                                             int R, int k0, int K, bool live, int tid, int chunk) {
+  constexpr int LDKS = TM + 4;
   if (VEC) {
     const int c = tid + chunk * NTHREADS;
     int row, kc, sm_off;
     if (MODE == KC) { row = c >> 3; kc = (c & 7) * 2; sm_off = row * LDKC + kc; }
-    else            { kc = c >> 6; row = (c & 63) * 2; sm_off = kc * LDKS + row; }
+    else            { kc = c / (TM / 2); row = (c % (TM / 2)) * 2; sm_off = kc * LDKS + row; }
     const int gr = r0 + row, gk = k0 + kc;
     // contiguous direction: k for KC, row for KS
     const int left = (MODE == KC) ? (K - gk) : (R - gr);
@@ -76,7 +86,7 @@ __device__ __forceinline__ void issue_chunk(double* __restrict__ s, const double
       const int e = tid + (2 * chunk + i) * NTHREADS;
       int row, kc, sm_off;
       if (MODE == KC) { row = e >> 4; kc = e & 15; sm_off = row * LDKC + kc; }
-      else            { kc = e >> 7; row = e & 127; sm_off = kc * LDKS + row; }
+      else            { kc = e / TM; row = e % TM; sm_off = kc * LDKS + row; }
       const int gr = r0 + row, gk = k0 + kc;
       const bool ok = live && (gr < R) && (gk < K);
       const long off = (MODE == KC) ? (long)gr * ld + gk : (long)gk * ld + gr;
@@ -86,8 +96,9 @@ __device__ __forceinline__ void issue_chunk(double* __restrict__ s, const double
 }
 
 template <int AMODE, int BMODE, bool KSCALE, bool VEC, class CFG>
-__global__ void __launch_bounds__(CFG::NTHREADS, 1) dgemm_kernel(const GemmParams p) {
+__global__ void __launch_bounds__(CFG::NTHREADS, CFG::CTAS_PER_SM) dgemm_kernel(const GemmParams p) {
   constexpr int MT = CFG::MT, NT = CFG::NT, NTHREADS = CFG::NTHREADS, VC = CFG::VC;
+  constexpr int TM = CFG::TM, LDKS = CFG::LDKS, TILE_DOUBLES = CFG::TILE_DOUBLES;
   constexpr int WM = MT * 8, WN = NT * 8;
   extern __shared__ __align__(16) double smem[];
   double* sA = smem;
@@ -117,7 +128,7 @@ __global__ void __launch_bounds__(CFG::NTHREADS, 1) dgemm_kernel(const GemmParam
   const long total_units = (long)p.ntiles * p.parts;
   long lu = blockIdx.x;
   bool lvalid = lu < total_units;
-  Unit lU = decode_unit(p, lvalid ? lu : 0);
+  Unit lU = decode_unit<TM>(p, lvalid ? lu : 0);
   int lk = 0;
   long mu = lu;
   bool mvalid = lvalid;
@@ -133,9 +144,9 @@ __global__ void __launch_bounds__(CFG::NTHREADS, 1) dgemm_kernel(const GemmParam
 #pragma unroll
     for (int sl = first; sl < last; ++sl) {
       if (sl < VC)
-        issue_chunk<AMODE, VEC, NTHREADS>(sA + stage * TILE_DOUBLES, p.A, p.lda, lU.m0, p.M, k0, p.K, lvalid, tid, sl);
+        issue_chunk<AMODE, VEC, NTHREADS, TM>(sA + stage * TILE_DOUBLES, p.A, p.lda, lU.m0, p.M, k0, p.K, lvalid, tid, sl);
       else if (sl < SLOTS)
-        issue_chunk<BMODE, VEC, NTHREADS>(sB + stage * TILE_DOUBLES, p.B, p.ldb, lU.n0, p.N, k0, p.K, lvalid, tid,
+        issue_chunk<BMODE, VEC, NTHREADS, TM>(sB + stage * TILE_DOUBLES, p.B, p.ldb, lU.n0, p.N, k0, p.K, lvalid, tid,
                                           sl - VC);
     }
   };
@@ -153,7 +164,7 @@ __global__ void __launch_bounds__(CFG::NTHREADS, 1) dgemm_kernel(const GemmParam
       lk = 0;
       lu += gridDim.x;
       lvalid = lu < total_units;
-      if (lvalid) lU = decode_unit(p, lu);
+      if (lvalid) lU = decode_unit<TM>(p, lu);
     }
   };
 
@@ -225,13 +236,13 @@ __global__ void __launch_bounds__(CFG::NTHREADS, 1) dgemm_kernel(const GemmParam
     if (++mk == mU.nkit) {
       // ------------------------------------------------------ epilogue ----
       if (p.parts > 1) {
-        double* ws = p.workspace + mu * (long)(BM * BN);
+        double* ws = p.workspace + mu * (long)(TM * TM);
 #pragma unroll
         for (int i = 0; i < MT; ++i)
 #pragma unroll
           for (int j = 0; j < NT; ++j) {
             const int r = wm0 + i * 8 + g, c = wn0 + j * 8 + 2 * tig;
-            *reinterpret_cast<double2*>(ws + r * BN + c) = make_double2(acc[i][j][0], acc[i][j][1]);
+            *reinterpret_cast<double2*>(ws + r * TM + c) = make_double2(acc[i][j][0], acc[i][j][1]);
           }
       } else {
         double cs[NT][2];
@@ -290,7 +301,7 @@ __global__ void __launch_bounds__(CFG::NTHREADS, 1) dgemm_kernel(const GemmParam
       mk = 0;
       mu += gridDim.x;
       mvalid = mu < total_units;
-      if (mvalid) mU = decode_unit(p, mu);
+      if (mvalid) mU = decode_unit<TM>(p, mu);
     }
   }
   cp_async_wait<0>();
@@ -300,13 +311,14 @@ __global__ void __launch_bounds__(CFG::NTHREADS, 1) dgemm_kernel(const GemmParam
 // same scaling/beta/lower/mirror rules as the direct epilogue.
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmParams p) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long per_tile = (long)BM * BN;
+  const int T = p.tile;
+  const long per_tile = (long)T * T;
   if (idx >= per_tile * p.ntiles) return;
   const int tile = (int)(idx / per_tile);
   const int e = (int)(idx % per_tile);
   int tm, tn;
   tile_coords(p, tile, tm, tn);
-  const int r = tm * BM + e / BN, c = tn * BN + e % BN;
+  const int r = tm * T + e / T, c = tn * T + e % T;
   if (r >= p.M || c >= p.N) return;
   if (p.lower && r < c) return;
   double s = 0.0;
@@ -324,48 +336,54 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmParams p) 
 template <int AMODE, int BMODE, bool KSCALE, bool VEC, class CFG>
 int launch_cfg(const GemmParams& p, int grid, cudaStream_t stream) {
   VT_CUDA(cudaFuncSetAttribute(dgemm_kernel<AMODE, BMODE, KSCALE, VEC, CFG>,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  dgemm_kernel<AMODE, BMODE, KSCALE, VEC, CFG><<<grid, CFG::NTHREADS, GEMM_SMEM_BYTES, stream>>>(p);
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::SMEM_BYTES));
+  dgemm_kernel<AMODE, BMODE, KSCALE, VEC, CFG><<<grid, CFG::NTHREADS, CFG::SMEM_BYTES, stream>>>(p);
   VT_LAUNCH_CHECK();
   return VT_OK;
 }
 
-using CfgDefault = GemmCfg<2, 4, true>;
+using CfgBig = GemmCfg<TILE_BIG, 2, 4, true, 1>;
+using CfgSmall = GemmCfg<TILE_SMALL, 2, 2, true, 2>;
 
-// VT_GEMM_CFG selects an alternative kernel configuration (tuning builds only).
-int tuning_cfg() {
-  static int cfg = -1;
-  if (cfg < 0) {
-    const char* e = getenv("VT_GEMM_CFG");
-    cfg = e ? atoi(e) : 0;
-  }
-  return cfg;
-}
+int ctas_per_sm(int tile) { return tile == TILE_SMALL ? CfgSmall::CTAS_PER_SM : CfgBig::CTAS_PER_SM; }
 
 template <int AMODE, int BMODE, bool KSCALE>
 int launch_variant(const GemmParams& p, int grid, cudaStream_t stream) {
   const bool vec = p.a_vec && p.b_vec;
-#ifdef VT_GEMM_TUNING
-  if (vec) {
-    switch (tuning_cfg()) {
-      case 1: return launch_cfg<AMODE, BMODE, KSCALE, true, GemmCfg<4, 4, true>>(p, grid, stream);
-      case 2: return launch_cfg<AMODE, BMODE, KSCALE, true, GemmCfg<4, 4, false>>(p, grid, stream);
-      case 3: return launch_cfg<AMODE, BMODE, KSCALE, true, GemmCfg<2, 4, false>>(p, grid, stream);
-      default: break;
-    }
+  if (p.tile == TILE_SMALL) {
+    if (vec) return launch_cfg<AMODE, BMODE, KSCALE, true, CfgSmall>(p, grid, stream);
+    return launch_cfg<AMODE, BMODE, KSCALE, false, CfgSmall>(p, grid, stream);
   }
-#endif
-  if (vec) return launch_cfg<AMODE, BMODE, KSCALE, true, CfgDefault>(p, grid, stream);
-  return launch_cfg<AMODE, BMODE, KSCALE, false, CfgDefault>(p, grid, stream);
+  if (vec) return launch_cfg<AMODE, BMODE, KSCALE, true, CfgBig>(p, grid, stream);
+  return launch_cfg<AMODE, BMODE, KSCALE, false, CfgBig>(p, grid, stream);
+}
+
+int count_tiles(int M, int N, int lower, int tile) {
+  const int tm = (M + tile - 1) / tile, tn = (N + tile - 1) / tile;
+  return lower ? tm * (tm + 1) / 2 : tm * tn;
 }
 
 }  // namespace
 
-int gemm_pick_parts(int ntiles, int kiters, size_t workspace_bytes) {
-  const int G = num_sms();
+// 128-wide tiles are the throughput configuration (half the L2->smem traffic per
+// flop).  64-wide tiles win when (a) the big tiles cannot occupy the machine
+// even with split-K (short K: Cholesky panels, trailing updates, solve steps),
+// or (b) they would execute >= 15% more flops than the small ones (ragged or
+// narrow outputs, the diagonal tiles of a small SYRK).
+int gemm_pick_tile(int M, int N, int K, int lower) {
+  const int kiters = (K + BK - 1) / BK;
+  const long nt_big = count_tiles(M, N, lower, TILE_BIG), nt_small = count_tiles(M, N, lower, TILE_SMALL);
+  const long max_parts = kiters / 8 > 0 ? kiters / 8 : 1;
+  if (nt_big * max_parts < num_sms()) return TILE_SMALL;
+  const double exec_big = (double)nt_big * TILE_BIG * TILE_BIG, exec_small = (double)nt_small * TILE_SMALL * TILE_SMALL;
+  return exec_big >= 1.15 * exec_small ? TILE_SMALL : TILE_BIG;
+}
+
+int gemm_pick_parts(int ntiles, int kiters, int tile, size_t workspace_bytes) {
+  const int G = num_sms() * ctas_per_sm(tile);
   if (ntiles >= 4 * G) return 1;
   long pmax = kiters / 8;                                  // at least 8 k-iterations per unit
-  const long by_ws = (long)(workspace_bytes / ((size_t)ntiles * BM * BN * 8));
+  const long by_ws = (long)(workspace_bytes / ((size_t)ntiles * tile * tile * 8));
   if (by_ws < pmax) pmax = by_ws;
   if (pmax > 4L * G) pmax = 4L * G;
   if (pmax < 2) return 1;
@@ -381,11 +399,11 @@ int gemm_pick_parts(int ntiles, int kiters, size_t workspace_bytes) {
 }
 
 size_t gemm_workspace_bytes(int M, int N, int K, int lower) {
-  const int tm = (M + BM - 1) / BM, tn = (N + BN - 1) / BN;
-  const int ntiles = lower ? tm * (tm + 1) / 2 : tm * tn;
+  const int tile = gemm_pick_tile(M, N, K, lower);
+  const int ntiles = count_tiles(M, N, lower, tile);
   const int kiters = (K + BK - 1) / BK;
-  const int P = gemm_pick_parts(ntiles, kiters, (size_t)1 << 62);
-  return P > 1 ? (size_t)ntiles * P * BM * BN * 8 : 0;
+  const int P = gemm_pick_parts(ntiles, kiters, tile, (size_t)1 << 62);
+  return P > 1 ? (size_t)ntiles * P * tile * tile * 8 : 0;
 }
 
 int gemm_launch(GemmParams p, cudaStream_t stream) {
@@ -393,22 +411,26 @@ int gemm_launch(GemmParams p, cudaStream_t stream) {
   if (p.M == 0 || p.N == 0) return VT_OK;
   VT_REQUIRE(p.A && p.B && p.C, "gemm: null operand");
   VT_REQUIRE(p.K > 0, "gemm: K must be positive");
-  p.tiles_m = (p.M + BM - 1) / BM;
-  p.tiles_n = (p.N + BN - 1) / BN;
+  VT_REQUIRE(p.tile == 0 || p.tile == TILE_BIG || p.tile == TILE_SMALL, "gemm: tile must be 0, %d or %d", TILE_BIG,
+             TILE_SMALL);
   if (p.lower) VT_REQUIRE(p.M == p.N, "gemm: lower-only output must be square");
+  if (p.tile == 0) p.tile = gemm_pick_tile(p.M, p.N, p.K, p.lower);
+  p.tiles_m = (p.M + p.tile - 1) / p.tile;
+  p.tiles_n = (p.N + p.tile - 1) / p.tile;
   p.ntiles = p.lower ? p.tiles_m * (p.tiles_m + 1) / 2 : p.tiles_m * p.tiles_n;
   p.kiters = (p.K + BK - 1) / BK;
   p.a_vec = (p.lda % 2 == 0) && (reinterpret_cast<uintptr_t>(p.A) % 16 == 0);
   p.b_vec = (p.ldb % 2 == 0) && (reinterpret_cast<uintptr_t>(p.B) % 16 == 0);
   p.c_vec = (p.ldc % 2 == 0) && (reinterpret_cast<uintptr_t>(p.C) % 16 == 0);
-  if (p.parts <= 0) p.parts = (p.workspace ? gemm_pick_parts(p.ntiles, p.kiters, p.workspace_bytes) : 1);
+  if (p.parts <= 0) p.parts = (p.workspace ? gemm_pick_parts(p.ntiles, p.kiters, p.tile, p.workspace_bytes) : 1);
   if (p.parts > p.kiters) p.parts = p.kiters;
   if (p.parts > 1)
-    VT_REQUIRE(p.workspace && p.workspace_bytes >= (size_t)p.ntiles * p.parts * BM * BN * 8,
+    VT_REQUIRE(p.workspace && p.workspace_bytes >= (size_t)p.ntiles * p.parts * p.tile * p.tile * 8,
                "gemm: split-K workspace too small (%zu bytes for %d parts x %d tiles)", p.workspace_bytes,
                p.parts, p.ntiles);
   const long units = (long)p.ntiles * p.parts;
-  const int grid = (int)(units < num_sms() ? units : num_sms());
+  const long slots = (long)num_sms() * ctas_per_sm(p.tile);
+  const int grid = (int)(units < slots ? units : slots);
   int st;
   if (p.kscale) {
     VT_REQUIRE(p.amode == KS && p.bmode == KS, "gemm: kscale is only implemented for KS x KS operands");
@@ -424,7 +446,7 @@ int gemm_launch(GemmParams p, cudaStream_t stream) {
   }
   if (st != VT_OK) return st;
   if (p.parts > 1) {
-    const long total = (long)p.ntiles * BM * BN;
+    const long total = (long)p.ntiles * p.tile * p.tile;
     splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p);
     VT_LAUNCH_CHECK();
   }

@@ -10,6 +10,10 @@
 //     SMSP saturate the pipe.
 //   * CTA tile 128x128x16, 8 warps as 2(M) x 4(N), warp tile 64x32 -> 32 DMMA
 //     per 12 LDS.64 per k4 step; 128 accumulator registers per thread.
+//     A second configuration (64x64x16, 4 warps as 2 x 2, two CTAs per SM)
+//     serves short-K / few-tile problems (Cholesky panels and trailing updates,
+//     triangular-solve steps) and outputs that 128-wide tiles cover wastefully
+//     (e.g. the 320 x 320 Schur complement of config 3).
 //   * Operands staged by 16-byte cp.async into a 4-stage ring.  Two operand
 //     layouts: KC (k contiguous in memory, smem [row][16+4]) and KS (k strided,
 //     i.e. the row index contiguous, smem [k][128+4]).  Both paddings are
@@ -27,12 +31,10 @@ namespace vt {
 
 enum OpMode : int { KC = 0, KS = 1 };
 
-constexpr int BM = 128, BN = 128, BK = 16;
-constexpr int LDKC = BK + 4;    // 20 doubles
-constexpr int LDKS = BM + 4;    // 132 doubles
-constexpr int TILE_DOUBLES = BM * LDKC;  // 2560 >= BK*LDKS = 2112
+constexpr int BK = 16;
+constexpr int LDKC = BK + 4;    // 20 doubles; the KS leading dimension is (tile + 4) doubles
 constexpr int STAGES = 4;
-constexpr int GEMM_SMEM_BYTES = (2 * STAGES * TILE_DOUBLES + STAGES * BK) * 8;
+constexpr int TILE_BIG = 128, TILE_SMALL = 64;   // CTA tile edge of the two kernel configurations
 
 struct GemmParams {
   int M, N, K;
@@ -46,6 +48,7 @@ struct GemmParams {
   int lower;       // only tiles with tile_m >= tile_n (square outputs)
   int mirror;      // lower only: also write C(n,m) = C(m,n) (symmetric result)
   int parts;       // split-K factor (>= 1); 0 = choose automatically
+  int tile;        // CTA tile edge: TILE_BIG, TILE_SMALL, or 0 = choose automatically
   double* workspace; size_t workspace_bytes;
   // derived (filled by gemm_launch)
   int tiles_m, tiles_n, ntiles, kiters, a_vec, b_vec, c_vec;
@@ -55,6 +58,8 @@ struct GemmParams {
 int gemm_launch(GemmParams p, cudaStream_t stream);
 // Workspace needed by gemm_launch for automatic split-K of this shape.
 size_t gemm_workspace_bytes(int M, int N, int K, int lower);
-int gemm_pick_parts(int ntiles, int kiters, size_t workspace_bytes);
+// Tile edge chosen for a shape when GemmParams::tile == 0.
+int gemm_pick_tile(int M, int N, int K, int lower);
+int gemm_pick_parts(int ntiles, int kiters, int tile, size_t workspace_bytes);
 
 }  // namespace vt

@@ -58,12 +58,14 @@ int vt_fp64_peak_probe(double seconds, double* tflops, void* stream);
  * (scale vectors may be NULL; kscale requires both operands in VT_OP_KS).
  * lower != 0: only the lower triangle of a square C is produced; mirror != 0
  * additionally writes the transposed entries (exactly symmetric result).
+ * `tile` selects the CTA tile edge (128: throughput configuration, 64: short-K
+ * / few-tile / ragged problems; 0: chosen from the shape).
  * Replaces the numpy `@` / einsum GEMMs at sensitivity_lib.py:67,76,247 and
  * lr_cov_lib.py:172 and is the engine under every routine below.            */
-size_t vt_dgemm_workspace_bytes(int M, int N, int K, int lower);
+size_t vt_dgemm_workspace_bytes(int M, int N, int K, int lower, int tile);
 int vt_dgemm(int M, int N, int K, double alpha, const double* A, int64_t lda, int amode, const double* B,
              int64_t ldb, int bmode, double beta, double* C, int64_t ldc, const double* kscale,
-             const double* colscale, const double* rowscale, int lower, int mirror, void* workspace,
+             const double* colscale, const double* rowscale, int lower, int mirror, int tile, void* workspace,
              size_t workspace_bytes, void* stream);
 
 /* ---- Hessian assembly ----------------------------------------------------
@@ -98,7 +100,8 @@ int vt_glm_dirderiv(const double* X, int64_t ldx, int64_t N, int D, const double
  * vt_potrf / vt_potrs replace scipy.linalg.cho_factor / cho_solve behind
  * get_dense_cholesky_solver (solver_lib.py:27,29).  A is overwritten by its
  * lower factor; `dinv` (vt_potrf_dinv_doubles(D) doubles) receives the inverted
- * 128x128 diagonal blocks used by the solve; *info (device int32) is 0 or the
+ * 128x128 diagonal blocks used by the solve (followed by a D x 128 scratch
+ * panel of the factorisation); *info (device int32) is 0 or the
  * 1-based column of the first non-positive pivot (LinAlgError upstream).
  * vt_potrs solves in place for a row-major D x K right-hand side.            */
 size_t vt_potrf_dinv_doubles(int D);

@@ -74,9 +74,10 @@ def test_cholesky_vs_scipy(vt, d, k):
     assert_close(L, np.linalg.cholesky(h), rtol=1e-9, atol_scale=1e-12)
 
 
+@pytest.mark.parametrize('tile', [0, 64, 128])
 @pytest.mark.parametrize('am,bm', [('KC', 'KC'), ('KC', 'KS'), ('KS', 'KC'), ('KS', 'KS')])
 @pytest.mark.parametrize('m,n,k', [(1, 1, 1), (5, 7, 3), (128, 128, 16), (130, 257, 1000), (300, 64, 4100)])
-def test_gemm_engine(vt, am, bm, m, n, k):
+def test_gemm_engine(vt, am, bm, m, n, k, tile):
     rng = np.random.RandomState(m + n + k)
     A = rng.normal(size=(m, k))
     B = rng.normal(size=(n, k))
@@ -85,6 +86,22 @@ def test_gemm_engine(vt, am, bm, m, n, k):
     Ad = _dev(A if am == 'KC' else A.T.copy())
     Bd = _dev(B if bm == 'KC' else B.T.copy())
     out = _dev(C0.copy())
-    vt.ops.gemm(Ad, Bd, am, bm, alpha=-0.5, beta=2.0, out=out, colscale=_dev(cs), rowscale=_dev(rs))
+    vt.ops.gemm(Ad, Bd, am, bm, alpha=-0.5, beta=2.0, out=out, colscale=_dev(cs), rowscale=_dev(rs), tile=tile)
     ref = -0.5 * (rs[:, None] * (A @ B.T) * cs[None, :]) + 2.0 * C0
     assert_close(out, ref, rtol=1e-10, atol_scale=1e-13)
+
+
+@pytest.mark.parametrize('tile', [0, 64, 128])
+@pytest.mark.parametrize('d,k', [(64, 40), (200, 5000), (320, 70000)])
+def test_gemm_lower_mirror_splitk(vt, d, k, tile):
+    """Symmetric rank-k update: lower tiles only, mirrored, deterministic split-K."""
+    rng = np.random.RandomState(d + k)
+    Z = rng.normal(size=(k, d))
+    ks = rng.uniform(0.5, 1.5, size=k)
+    Zd = _dev(Z)
+    out = vt.ops.gemm(Zd, Zd, 'KS', 'KS', kscale=_dev(ks), lower=True, mirror=True, tile=tile)
+    out2 = vt.ops.gemm(Zd, Zd, 'KS', 'KS', kscale=_dev(ks), lower=True, mirror=True, tile=tile)
+    assert torch.equal(out, out2)
+    o = out.cpu().numpy()
+    assert np.array_equal(o, o.T)
+    assert_close(o, (Z * ks[:, None]).T @ Z, rtol=1e-10, atol_scale=1e-13)

@@ -87,11 +87,13 @@ int vt_fp64_peak_probe(double seconds, double* tflops, void* stream) {
   return st;
 }
 
-size_t vt_dgemm_workspace_bytes(int M, int N, int K, int lower) { return gemm_workspace_bytes(M, N, K, lower); }
+size_t vt_dgemm_workspace_bytes(int M, int N, int K, int lower, int tile) {
+  return gemm_workspace_bytes(M, N, K, lower, tile);
+}
 
 int vt_dgemm(int M, int N, int K, double alpha, const double* A, int64_t lda, int amode, const double* B,
              int64_t ldb, int bmode, double beta, double* C, int64_t ldc, const double* kscale,
-             const double* colscale, const double* rowscale, int lower, int mirror, void* workspace,
+             const double* colscale, const double* rowscale, int lower, int mirror, int tile, void* workspace,
              size_t workspace_bytes, void* stream) {
   VT_REQUIRE((amode == KC || amode == KS) && (bmode == KC || bmode == KS), "dgemm: bad operand mode");
   GemmParams p{};
@@ -103,13 +105,14 @@ int vt_dgemm(int M, int N, int K, double alpha, const double* A, int64_t lda, in
   p.kscale = kscale; p.colscale = colscale; p.rowscale = rowscale;
   p.lower = lower; p.mirror = mirror;
   p.parts = 0;
+  p.tile = tile;
   p.workspace = static_cast<double*>(workspace);
   p.workspace_bytes = workspace_bytes;
   return gemm_launch(p, S(stream));
 }
 
 size_t vt_syrk_workspace_bytes(int64_t N, int D) {
-  return gemm_workspace_bytes(D, D, (int)(N > 2147483647LL ? 2147483647LL : N), 1);
+  return gemm_workspace_bytes(D, D, (int)(N > 2147483647LL ? 2147483647LL : N), 1, 0);
 }
 
 int vt_syrk_weighted(const double* X, int64_t ldx, int64_t N, int D, const double* s, double l2, double* H,

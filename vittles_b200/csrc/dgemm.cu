@@ -398,8 +398,8 @@ int gemm_pick_parts(int ntiles, int kiters, int tile, size_t workspace_bytes) {
   return best;
 }
 
-size_t gemm_workspace_bytes(int M, int N, int K, int lower) {
-  const int tile = gemm_pick_tile(M, N, K, lower);
+size_t gemm_workspace_bytes(int M, int N, int K, int lower, int tile) {
+  if (tile == 0) tile = gemm_pick_tile(M, N, K, lower);
   const int ntiles = count_tiles(M, N, lower, tile);
   const int kiters = (K + BK - 1) / BK;
   const int P = gemm_pick_parts(ntiles, kiters, tile, (size_t)1 << 62);

@@ -57,7 +57,7 @@ struct GemmParams {
 // Fills the derived fields, picks `parts` if 0 and launches on `stream`.
 int gemm_launch(GemmParams p, cudaStream_t stream);
 // Workspace needed by gemm_launch for automatic split-K of this shape.
-size_t gemm_workspace_bytes(int M, int N, int K, int lower);
+size_t gemm_workspace_bytes(int M, int N, int K, int lower, int tile);
 // Tile edge chosen for a shape when GemmParams::tile == 0.
 int gemm_pick_tile(int M, int N, int K, int lower);
 int gemm_pick_parts(int ntiles, int kiters, int tile, size_t workspace_bytes);

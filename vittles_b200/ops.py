@@ -70,10 +70,11 @@ def fp64_peak_probe(seconds=0.3):
 
 # ------------------------------------------------------------------ GEMM ----
 def gemm(A, B, amode='KC', bmode='KC', alpha=1.0, beta=0.0, out=None, M=None, N=None, K=None,
-         kscale=None, colscale=None, rowscale=None, lower=False, mirror=False):
+         kscale=None, colscale=None, rowscale=None, lower=False, mirror=False, tile=0):
     """out(m,n) = alpha * rs[m] cs[n] sum_k ks[k] A(m,k) B(n,k) + beta * out.
 
-    ``KC``: the tensor is (rows, K); ``KS``: the tensor is (K, rows)."""
+    ``KC``: the tensor is (rows, K); ``KS``: the tensor is (K, rows).  ``tile``:
+    CTA tile edge (128 or 64), 0 = chosen from the shape."""
     lib = _cabi.require_cuda()
     _mat(A, 'A'); _mat(B, 'B')
     am = _cabi.OP_KC if amode == 'KC' else _cabi.OP_KS
@@ -90,10 +91,10 @@ def gemm(A, B, amode='KC', bmode='KC', alpha=1.0, beta=0.0, out=None, M=None, N=
             raise ValueError('gemm: beta != 0 needs `out`')
         out = torch.empty((M, N), dtype=torch.float64, device=A.device)
     _mat(out, 'out')
-    wsb = lib.vt_dgemm_workspace_bytes(M, N, K, int(lower))
+    wsb = lib.vt_dgemm_workspace_bytes(M, N, K, int(lower), int(tile))
     ws, wsb = _ws('gemm', wsb, A.device)
     check(lib.vt_dgemm(M, N, K, float(alpha), ptr(A), _ld(A), am, ptr(B), _ld(B), bm, float(beta), ptr(out),
-                       _ld(out), ptr(kscale), ptr(colscale), ptr(rowscale), int(lower), int(mirror), ptr(ws), wsb,
+                       _ld(out), ptr(kscale), ptr(colscale), ptr(rowscale), int(lower), int(mirror), int(tile), ptr(ws), wsb,
                        stream()))
     return out
 

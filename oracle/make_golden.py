@@ -52,7 +52,7 @@ from vittles import solver_lib as ref_solver_lib  # noqa: E402
 from vittles import sensitivity_lib as ref_sens  # noqa: E402
 
 import oracle  # noqa: E402
-from oracle import models, fixtures  # noqa: E402
+from oracle import models, fixtures, bivariate  # noqa: E402,F401
 
 assert vittles.__file__.startswith('/root/reference'), vittles.__file__
 
@@ -338,6 +338,100 @@ def golden_lr_cov():
          hessian=lr.get_hessian_at_opt(), cov=cov, jac=jac, cross01_23=cross)
 
 
+# --------------------------------------------------------------------------
+def golden_bivariate():
+    """tests/test_bivariate_sensitivity_lib.py:15-260 on a seeded version of its model
+    (y ~ N(exp(x theta), 1), weights as the second hyperparameter), at an
+    incompletely optimised theta, plus a Poisson GLM for the structured path."""
+    import autograd
+    from vittles.bivariate_sensitivity_lib import CrossSensitivity, OptimumChecker
+    rng = np.random.RandomState(2024)
+    dim, n_obs = 10, 200
+    theta_true = rng.random_sample(dim) - 0.5
+    x = rng.random_sample((n_obs, dim))
+    x = x - np.mean(x, axis=0)
+    y = np.exp(x @ theta_true) + rng.normal(size=n_obs)
+    xt, yt = torch.as_tensor(x), torch.as_tensor(y)
+
+    def w_obj(theta, w):
+        resid = yt - torch.exp(xt @ theta)
+        return 0.5 * torch.sum(w * resid ** 2)
+
+    def pert_obj(theta, lam, w):
+        return w_obj(theta, w) - torch.dot(lam, theta)
+
+    w_base = np.ones(n_obs)
+    theta = np.zeros(dim)
+    grad_f = torch.func.grad(w_obj, argnums=0)
+    hess_f = torch.func.hessian(w_obj, argnums=0)
+    for _ in range(50):
+        theta = theta - np.linalg.solve(hess_f(torch.as_tensor(theta), torch.as_tensor(w_base)).numpy(),
+                                        grad_f(torch.as_tensor(theta), torch.as_tensor(w_base)).numpy())
+    assert np.linalg.norm(grad_f(torch.as_tensor(theta), torch.as_tensor(w_base)).numpy()) < 1e-10
+    theta_base = theta + 0.02 * (rng.random_sample(dim) - 0.5)          # "stopped early"
+    hess_base = hess_f(torch.as_tensor(theta_base), torch.as_tensor(w_base)).numpy()
+    lam_base = grad_f(torch.as_tensor(theta_base), torch.as_tensor(w_base)).numpy()
+    new_w = np.ones(n_obs)
+    new_w[1] = 0
+    new_w[17] = 2.5
+    dw = new_w - w_base
+    dlambda = -1 * lam_base
+
+    def solver(v):
+        return np.linalg.solve(hess_base, v)
+    g3 = autograd.jacobian(pert_obj, argnum=0)
+    g3_t = torch.func.grad(pert_obj, argnums=0)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        cs = CrossSensitivity(estimating_equation=g3, solver=solver, input_base=theta_base,
+                              hyper1_base=lam_base, hyper2_base=w_base)
+    di1, di2 = cs.get_di1(dlambda), cs.get_di2(dw)
+    cross = cs.evaluate(dlambda, dw)
+    o_cross, o_di1, o_di2 = oracle.bivariate.cross_sensitivity(g3_t, solver, theta_base, lam_base, w_base, dlambda, dw)
+    close(o_di1, di1, 'bivariate di1')
+    close(o_di2, di2, 'bivariate di2')
+    close(o_cross, cross, 'bivariate cross')
+    # the reference test's own assertions (:243-257)
+    g2 = autograd.jacobian(w_obj, argnum=0)
+    g2_t = torch.func.grad(w_obj, argnums=0)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        oc = OptimumChecker(estimating_equation=g2, solver=solver, input_base=theta_base, hyper_base=w_base)
+    newton_step = -1 * np.linalg.solve(hess_base, lam_base)
+    np.testing.assert_array_almost_equal(newton_step, oc.get_newton_step())
+    oc_out = dict(newton_step=oc.get_newton_step(), dinput_dhyper=oc.get_dinput_dhyper(dw),
+                  correction=oc.correction(new_w), evaluate=oc.evaluate(new_w))
+    o_oc = oracle.bivariate.optimum_checker(g2_t, solver, theta_base, w_base, new_w)
+    for k in oc_out:
+        close(o_oc[k], oc_out[k], 'optimum checker ' + k)
+    out = dict(x=x, y=y, theta_base=theta_base, hess_base=hess_base, lam_base=lam_base, new_w=new_w,
+               di1=di1, di2=di2, cross=cross, **{'oc_' + k: v for k, v in oc_out.items()})
+
+    # Poisson GLM (structured objective family of this build) away from its optimum
+    Xp = models.synth_design(31, 0, 300, 6)
+    yp = rng.poisson(np.exp(Xp @ (0.5 * models.synth_theta(31, 6)))).astype(np.float64)
+    wp = rng.uniform(0.5, 1.5, size=300)
+    fp = models.glm_objective(Xp, yp, family='poisson', l2=0.2)
+    thp = models.glm_newton(Xp, yp, wp, family='poisson', l2=0.2) + 0.01 * (rng.random_sample(6) - 0.5)
+    Hp = torch.func.hessian(fp, argnums=0)(torch.as_tensor(thp), torch.as_tensor(wp)).numpy()
+    new_wp = wp * rng.uniform(0.8, 1.2, size=300)
+
+    def solver_p(v):
+        return np.linalg.solve(Hp, v)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        ocp = OptimumChecker(estimating_equation=autograd.jacobian(fp, argnum=0), solver=solver_p,
+                             input_base=thp, hyper_base=wp)
+    ocp_out = dict(newton_step=ocp.get_newton_step(), dinput_dhyper=ocp.get_dinput_dhyper(new_wp - wp),
+                   correction=ocp.correction(new_wp), evaluate=ocp.evaluate(new_wp))
+    o_ocp = oracle.bivariate.optimum_checker(torch.func.grad(fp, argnums=0), solver_p, thp, wp, new_wp)
+    for k in ocp_out:
+        close(o_ocp[k], ocp_out[k], 'poisson optimum checker ' + k)
+    out.update(p_X=Xp, p_y=yp, p_w=wp, p_l2=np.array(0.2), p_theta=thp, p_hess=Hp, p_new_w=new_wp,
+               **{'p_oc_' + k: v for k, v in ocp_out.items()})
+    save('bivariate', **out)
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     torch.set_default_dtype(torch.float64)
@@ -347,4 +441,5 @@ if __name__ == '__main__':
     golden_taylor()
     golden_sparse_hessian()
     golden_lr_cov()
+    golden_bivariate()
     print('all golden fixtures written; oracle == reference on every case')

@@ -63,3 +63,33 @@ def test_lr_cov_dense_closed_form(vt, dim, k):
     # mean moments recover the true covariance exactly
     Jm = np.hstack([np.eye(dim), np.zeros((dim, dim))])
     assert_close(lr.get_lr_covariance_from_jacobians(Jm, Jm), true_cov, rtol=1e-8, atol_scale=1e-11)
+
+
+def test_lr_cov_without_factorisation(vt, golden):
+    """factorize_hessian=False (documented upstream at lr_cov_lib.py:67-70, never implemented
+    there): CG over Hessian-vector products, no Hessian formed; same covariances."""
+    g = golden('lr_cov')
+
+    def f_dev(par):
+        tm = torch.as_tensor(g['true_mean'], device=par.device)
+        ti = torch.as_tensor(g['true_info'], device=par.device)
+        mean, var = par[:4], par[4:]
+        tc = mean - tm
+        return -1 * (0.5 * torch.sum(torch.log(var)) - 0.5 * (torch.sum(torch.diagonal(ti) * var) + tc @ ti @ tc))
+    for hess in (None, g['hessian']):
+        lr = vt.LinearResponseCovariances(f_dev, g['opt'], validate_optimum=True, hessian_at_opt=hess,
+                                          factorize_hessian=False, grad_tol=1e-12)
+        assert lr._hess0 is hess                      # nothing formed behind the caller's back
+        assert_close(lr.get_lr_covariance(lambda par: par[:4]), g['true_cov'], rtol=1e-8)
+        assert_close(lr.get_hessian_at_opt(), g['hessian'], rtol=1e-9, atol_scale=1e-12)
+    with pytest.raises(ValueError):
+        vt.LinearResponseCovariances(f_dev, g['opt'] + 0.01, validate_optimum=True, factorize_hessian=False,
+                                     grad_tol=1e-12)
+    # larger, supplied Hessian: the operator is the GEMV kernel
+    rng = np.random.RandomState(5)
+    dim = 300
+    a = rng.normal(size=(dim, dim + 3))
+    H = a @ a.T / dim + np.eye(dim)
+    J = rng.normal(size=(7, dim))
+    lr = vt.LinearResponseCovariances(lambda par: par.sum(), np.zeros(dim), hessian_at_opt=H, factorize_hessian=False)
+    assert_close(lr.get_lr_covariance_from_jacobians(J, J), J @ np.linalg.solve(H, J.T), rtol=1e-8, atol_scale=1e-10)

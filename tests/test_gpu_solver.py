@@ -105,3 +105,20 @@ def test_gemm_lower_mirror_splitk(vt, d, k, tile):
     o = out.cpu().numpy()
     assert np.array_equal(o, o.T)
     assert_close(o, (Z * ks[:, None]).T @ Z, rtol=1e-10, atol_scale=1e-13)
+
+
+def test_cg_solver_matrix_rhs(vt):
+    """Extension over scipy/the reference: a (dim, K) right-hand side is solved column by column."""
+    rng = np.random.RandomState(11)
+    d = 40
+    a = rng.normal(size=(d, d + 2))
+    h = a @ a.T / d + np.eye(d)
+    hd = _dev(h)
+    solve = vt.solver_lib.get_cg_solver(lambda v: hd @ v if isinstance(v, torch.Tensor) else h @ v, d,
+                                        cg_opts={'tol': 1e-13})
+    B = rng.normal(size=(d, 3))
+    assert_close(solve(B), np.linalg.solve(h, B), rtol=1e-8, atol_scale=1e-11)
+    out = solve(_dev(B))
+    assert isinstance(out, torch.Tensor) and out.is_cuda and out.shape == (d, 3)
+    with pytest.raises(ValueError):
+        solve(rng.normal(size=(d + 1, 3)))

@@ -145,6 +145,35 @@ def test_lr_cov_oracle_vs_golden(golden):
         oracle.lr_cov.base_values(f, g['opt'] + 0.01, validate=True, grad_tol=1e-12)
 
 
+def test_bivariate_oracle_vs_golden(golden):
+    """CrossSensitivity / OptimumChecker restatement vs the unmodified reference
+    (bivariate_sensitivity_lib.py:57-115,118-205)."""
+    import torch
+    from oracle import bivariate
+    g = golden('bivariate')
+    xt, yt = torch.as_tensor(g['x']), torch.as_tensor(g['y'])
+
+    def w_obj(theta, w):
+        return 0.5 * torch.sum(w * (yt - torch.exp(xt @ theta)) ** 2)
+
+    def pert_obj(theta, lam, w):
+        return w_obj(theta, w) - torch.dot(lam, theta)
+
+    def solver(v):
+        return np.linalg.solve(g['hess_base'], v)
+    w_base = np.ones(len(g['y']))
+    cross, di1, di2 = bivariate.cross_sensitivity(torch.func.grad(pert_obj, argnums=0), solver, g['theta_base'],
+                                                  g['lam_base'], w_base, -g['lam_base'], g['new_w'] - w_base)
+    assert_close(di1, g['di1'], rtol=1e-10)
+    assert_close(di2, g['di2'], rtol=1e-10)
+    assert_close(cross, g['cross'], rtol=1e-10)
+    oc = bivariate.optimum_checker(torch.func.grad(w_obj, argnums=0), solver, g['theta_base'], w_base, g['new_w'])
+    for k in ('newton_step', 'dinput_dhyper', 'correction', 'evaluate'):
+        assert_close(oc[k], g['oc_' + k], rtol=1e-10, atol_scale=1e-11)
+    # the reference test's own check: the Lagrange direction reproduces a Newton step
+    assert_close(oc['newton_step'], -np.linalg.solve(g['hess_base'], g['lam_base']), rtol=1e-10)
+
+
 def test_synth_generator_statistics():
     X = models.synth_design(1, 0, 4000, 64)
     assert abs(X.mean()) < 2e-3 and abs(X.var() * 64 - 1.0) < 0.02

@@ -11,6 +11,7 @@ from .sensitivity_lib import \
 from .sparse_hessian_lib import SparseBlockHessian
 from .lr_cov_lib import LinearResponseCovariances
 from . import solver_lib
+from . import bivariate_sensitivity_lib
 from . import objectives
 from . import ops
 

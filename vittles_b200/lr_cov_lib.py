@@ -3,6 +3,11 @@
 ``Cov_LR(g1, g2) = J1 H^{-1} J2^T``: the Hessian is factorised by the GPU
 Cholesky (``vt_potrf``), ``H^{-1} J2^T`` is a multi-right-hand-side ``vt_potrs``
 and the final product runs on the FP64 tensor-core GEMM engine.
+
+``factorize_hessian=False`` - documented upstream (``lr_cov_lib.py:67-70``) but
+never implemented there (``:106`` always factorises) - is honoured here
+(SURVEY.md section 8f item 2): the Hessian is not formed and every solve is a
+conjugate-gradient run (``vt_cg_*`` kernels) over Hessian-vector products.
 """
 from copy import deepcopy
 
@@ -19,6 +24,11 @@ class LinearResponseCovariances:
     callable of the flat parameter (or a structured objective exposing
     ``vt_hessian`` / ``vt_grad``)."""
 
+    #: options of the conjugate-gradient solver used when ``factorize_hessian=False``
+    #: (see :func:`vittles_b200.solver_lib.get_cg_solver`); tighter than scipy's default
+    #: 1e-5 because a covariance is a difference-sensitive quantity
+    cg_opts = {'tol': 1e-10}
+
     def __init__(self, objective_fun, opt_par_value, validate_optimum=False, hessian_at_opt=None,
                  factorize_hessian=True, grad_tol=1e-8):
         self._obj_fun = objective_fun
@@ -33,20 +43,24 @@ class LinearResponseCovariances:
         self.set_base_values(opt_par_value, hessian_at_opt, factorize_hessian, validate=validate_optimum)
 
     def set_base_values(self, opt_par_value, hessian_at_opt, factorize_hessian=True, validate=True, grad_tol=None):
-        """Reference ``:88-119``.  ``factorize_hessian`` is accepted and, as
-        upstream (``:106``), the Cholesky solver is always used.  Validation is
-        on the Newton step ``||H^{-1} grad||`` (``:108-119``)."""
+        """Reference ``:88-119``.  With ``factorize_hessian=True`` (default) the
+        Hessian is formed (unless given) and factorised by the GPU Cholesky, as
+        upstream (``:106``).  With ``False`` the solver is conjugate gradients
+        over Hessian-vector products and no Hessian is formed (a supplied
+        ``hessian_at_opt`` is used as the operator).  Validation is on the
+        Newton step ``||H^{-1} grad||`` (``:108-119``)."""
         if grad_tol is None:
             grad_tol = self._grad_tol
         self._kind = kind_of(opt_par_value)
         self._opt0 = to_device(deepcopy(opt_par_value)).reshape(-1)
-        if hessian_at_opt is None:
-            self._hess0 = self._obj_fun_hessian(self._opt0)
-            self._hess_kind = self._kind
+        self._hess_kind = self._kind if hessian_at_opt is None else None
+        if factorize_hessian:
+            self._hess0 = self._obj_fun_hessian(self._opt0) if hessian_at_opt is None else hessian_at_opt
+            self.hess_solver = solver_lib.get_cholesky_solver(self._hess0)
         else:
-            self._hess0 = hessian_at_opt
-            self._hess_kind = None
-        self.hess_solver = solver_lib.get_cholesky_solver(self._hess0)
+            self._hess0 = hessian_at_opt                 # None: formed only if get_hessian_at_opt() is called
+            self.hess_solver = solver_lib.get_cg_solver(self._hvp_operator(hessian_at_opt), len(self._opt0),
+                                                        cg_opts=dict(self.cg_opts))
         if validate:
             grad0 = self._obj_fun_grad(self._opt0)
             newton_step = -1 * to_device(self.hess_solver(grad0), self._opt0.device)
@@ -56,7 +70,22 @@ class LinearResponseCovariances:
                     'The gradient is not zero at the proposed optimal values.  '
                     '||newton_step|| = {} > {} = grad_tol'.format(newton_step_norm, grad_tol))
 
+    def _hvp_operator(self, hessian_at_opt):
+        """``v -> H v`` on device tensors without forming H: the structured
+        objective's fused pass, a GEMV with a supplied Hessian, or forward-over-
+        reverse autodiff of the generic objective."""
+        dev = self._opt0.device
+        if hessian_at_opt is not None:
+            H = to_device(hessian_at_opt, dev).contiguous()
+            return lambda v: ops.gemv(H, to_device(v, dev))
+        if self._structured and hasattr(self._obj_fun, 'vt_hvp_fn'):
+            return self._obj_fun.vt_hvp_fn(self._opt0)
+        x0 = self._opt0
+        return lambda v: tf.jvp(self._obj_fun_grad, (x0,), (to_device(v, dev),))[1]
+
     def get_hessian_at_opt(self):
+        if self._hess0 is None:                           # factorize_hessian=False: formed on request only
+            self._hess0 = self._obj_fun_hessian(self._opt0)
         return self._hess0 if self._hess_kind is None else as_kind(self._hess0, self._hess_kind)
 
     def get_lr_covariance_from_jacobians(self, moment_jacobian1, moment_jacobian2):

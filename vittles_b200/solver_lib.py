@@ -84,7 +84,13 @@ def get_cg_solver(mat_times_vec, dim, cg_opts={}):
     CUDA tensor if ``v`` is one, numpy if ``v`` is numpy).
 
     Supported ``cg_opts``: ``tol`` / ``rtol``, ``atol``, ``maxiter``, ``x0``,
-    ``callback``.  A preconditioner ``M`` is not implemented."""
+    ``callback``.  A preconditioner ``M`` is not implemented.
+
+    Extension: a ``(dim, K)`` right-hand side is
+    solved column by column, so the closure can stand in for the Cholesky one
+    at the matrix-RHS call sites (``sensitivity_lib.py:226``,
+    ``lr_cov_lib.py:172``); scipy's CG, hence the reference, accepts vectors
+    only."""
     opts = dict(cg_opts)
     if 'M' in opts and opts['M'] is not None:
         raise NotImplementedError('get_cg_solver: preconditioner `M` is not implemented on the GPU path')
@@ -97,6 +103,12 @@ def get_cg_solver(mat_times_vec, dim, cg_opts={}):
     callback = opts.get('callback', None)
 
     def solve(v):
+        if getattr(v, 'ndim', 1) == 2 and v.shape[1] != 1:
+            if v.shape[0] != dim:
+                raise ValueError('right-hand side has shape {}, expected ({}, K)'.format(tuple(v.shape), dim))
+            vd = to_device(v)
+            cols = [to_device(solve(vd[:, k].contiguous()), vd.device) for k in range(vd.shape[1])]
+            return as_kind(torch.stack(cols, dim=1), kind_of(v))
         kind = kind_of(v)
         b = to_device(v).reshape(-1).contiguous()
         if b.numel() != dim:

@@ -111,3 +111,45 @@ def test_bench_reference_arm_runs_on_cpu():
     line = json.loads(out.strip().splitlines()[-1])
     assert line['impl'] == 'reference' and line['value'] > 0 and line['cpu_baseline']['kind'] == 'port'
     assert line['e2e']['h2d_bytes_per_step'] == 0
+
+
+def test_block_arrow_detection_host_logic():
+    """detect_block_arrow: recovers the blocks of a permuted block-arrow COO
+    matrix, sums duplicate entries, and rejects matrices without that structure."""
+    import scipy.sparse
+    from vittles_b200.sparse_hessian_lib import detect_block_arrow
+    rng = np.random.RandomState(0)
+    G, M, Dg = 40, 5, 90
+    d = G * M + Dg
+    perm = rng.permutation(d)
+    sa, gi = perm[:G * M].reshape(G, M), np.sort(perm[G * M:])
+    dense = np.zeros((d, d))
+    blocks = rng.normal(size=(G, M, M))
+    blocks = blocks + blocks.transpose(0, 2, 1) + 10 * np.eye(M)
+    cross = rng.normal(size=(G, M, Dg))
+    hgg = rng.normal(size=(Dg, Dg))
+    hgg = hgg + hgg.T
+    for g in range(G):
+        dense[np.ix_(sa[g], sa[g])] = blocks[g]
+        dense[np.ix_(sa[g], gi)] = cross[g]
+        dense[np.ix_(gi, sa[g])] = cross[g].T
+    dense[np.ix_(gi, gi)] = hgg
+    coo = scipy.sparse.coo_matrix(dense)
+    # duplicates: split every value into two halves, as the reference's assembly does (:147-153)
+    dup = scipy.sparse.coo_matrix((np.concatenate([coo.data / 2, coo.data / 2]),
+                                   (np.concatenate([coo.row, coo.row]), np.concatenate([coo.col, coo.col]))), (d, d))
+    for mat in (coo, dup):
+        sa2, gi2, b2, c2, h2 = detect_block_arrow(mat)
+        assert np.array_equal(gi2, gi)
+        rebuilt = np.zeros((d, d))
+        for g in range(sa2.shape[0]):
+            rebuilt[np.ix_(sa2[g], sa2[g])] = b2[g]
+            rebuilt[np.ix_(sa2[g], gi2)] = c2[g]
+            rebuilt[np.ix_(gi2, sa2[g])] = c2[g].T
+        rebuilt[np.ix_(gi2, gi2)] = h2
+        np.testing.assert_allclose(rebuilt, dense, rtol=0, atol=1e-15)
+        assert sa2.shape == (G, M)
+    r = scipy.sparse.random(80, 80, density=0.1, random_state=2)
+    assert detect_block_arrow((r @ r.T + scipy.sparse.eye(80)).tocoo()) is None
+    ragged = scipy.sparse.block_diag([np.ones((3, 3)), np.ones((4, 4))])
+    assert detect_block_arrow(ragged) is None

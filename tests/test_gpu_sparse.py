@@ -146,6 +146,45 @@ def test_block_arrow_solver_well_conditioned(vt):
     assert_close(out, ref[:, 0], rtol=1e-8, atol_scale=1e-11)
 
 
+def test_scipy_sparse_arrow_is_recognised(vt):
+    """a scipy COO block-arrow matrix (the form the reference's SparseBlockHessian
+    returns and hands to SuperLU) is routed to the batched block + Schur kernels."""
+    import scipy.sparse
+    from vittles_b200.sparse_hessian_lib import BlockArrowHessian
+    rng = np.random.RandomState(3)
+    G, M, Dg = 120, 7, 150
+    d = G * M + Dg
+    perm = rng.permutation(d)
+    sa, gi = perm[:G * M].reshape(G, M), perm[G * M:]
+    a = rng.normal(size=(G, M, M))
+    blocks = a @ a.transpose(0, 2, 1) / M + np.eye(M)
+    cross = 0.02 * rng.normal(size=(G, M, Dg))
+    g0 = rng.normal(size=(Dg, Dg))
+    hgg = g0 @ g0.T / Dg + 3.0 * np.eye(Dg)
+    h = BlockArrowHessian(d, torch.as_tensor(sa, device='cuda'), torch.as_tensor(gi, device='cuda'),
+                          blocks=_dev(blocks), cross=_dev(cross), hgg=_dev(hgg))
+    coo = h.tocoo()
+    assert scipy.sparse.issparse(coo)
+    solve = vt.solver_lib.get_cholesky_solver(coo)
+    assert hasattr(solve, 'block_arrow')                      # not densified
+    assert solve.block_arrow.sparsity_array.shape == (G, M)
+    B = rng.normal(size=(d, 2))
+    ref = np.linalg.solve(coo.toarray(), B)
+    assert_close(solve(B), ref, rtol=1e-8, atol_scale=1e-11)
+    assert_close(solve(B[:, 1]), ref[:, 1], rtol=1e-8, atol_scale=1e-11)
+    # block diagonal only (reference test shape: 10 blocks of 9), and an unstructured matrix
+    bd = scipy.sparse.block_diag([blocks[g] for g in range(10)]).tocoo()
+    s2 = vt.solver_lib.get_cholesky_solver(bd)
+    assert hasattr(s2, 'block_arrow')
+    b2 = rng.normal(size=70)
+    assert_close(s2(b2), np.linalg.solve(bd.toarray(), b2), rtol=1e-8, atol_scale=1e-11)
+    r = scipy.sparse.random(60, 60, density=0.2, random_state=1)
+    spd = (r @ r.T + 5.0 * scipy.sparse.eye(60)).tocoo()
+    s3 = vt.solver_lib.get_cholesky_solver(spd)
+    assert not hasattr(s3, 'block_arrow')
+    assert_close(s3(b2[:60]), np.linalg.solve(spd.toarray(), b2[:60]), rtol=1e-8, atol_scale=1e-11)
+
+
 def test_block_kernels_directly(vt):
     rng = np.random.RandomState(0)
     for (G, M, Dg) in [(1, 1, 1), (37, 19, 320), (1000, 32, 7), (5, 2, 1030)]:

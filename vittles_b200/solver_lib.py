@@ -48,14 +48,22 @@ def get_sparse_cholesky_solver(h):
 
     ``ValueError`` unless ``h`` is sparse (``:46-47``).  A block-arrow Hessian
     produced by :class:`vittles_b200.SparseBlockHessian` is factorised with the
-    batched block-Cholesky + Schur-complement kernels; any other scipy sparse
-    matrix is densified and factorised with the dense GPU Cholesky (the matrix
-    must be symmetric positive definite, as the reference's name promises)."""
+    batched block-Cholesky + Schur-complement kernels; so is a scipy sparse
+    matrix in which that structure is recognised
+    (:meth:`BlockArrowHessian.from_sparse`, e.g. the reference's own
+    ``coo_matrix`` Hessians).  Any other scipy sparse matrix is densified and
+    factorised with the dense GPU Cholesky (the matrix must be symmetric
+    positive definite, as the reference's name promises)."""
     from .sparse_hessian_lib import BlockArrowHessian
     if isinstance(h, BlockArrowHessian):
         return h.get_solver()
     if not sp.sparse.issparse(h):
         raise ValueError('`h` must be sparse.')
+    arrow = BlockArrowHessian.from_sparse(h)
+    if arrow is not None:
+        solve = arrow.get_solver()
+        solve.block_arrow = arrow
+        return solve
     if h.shape[0] > 32768:
         raise ValueError('get_sparse_cholesky_solver: a general sparse matrix of dimension {} is too large to '
                          'densify; build it with SparseBlockHessian to use the block-arrow solver.'.format(h.shape[0]))

@@ -22,6 +22,51 @@ from ._arrays import to_device, kind_of, as_kind
 from .objectives import StructuredObjective
 
 
+def detect_block_arrow(h, max_block=32):
+    """Host-side structure detection for :meth:`BlockArrowHessian.from_sparse`.
+
+    Global indices are the rows that touch more than half of the columns; the
+    remaining rows (at least as many as the global ones) must fall into two or
+    more connected components of one common size ``M <= max_block`` that are
+    coupled only to themselves and to the global rows.  Returns ``(sparsity_array (G, M), global_inds (Dg,), blocks (G, M, M),
+    cross (G, M, Dg) | None, hgg (Dg, Dg) | None)`` as numpy arrays, or ``None``.
+    Duplicate COO entries are summed, as scipy does (the reference relies on
+    that, ``sparse_hessian_lib.py:147-153``)."""
+    from scipy.sparse import csgraph
+    a = scipy.sparse.csr_matrix(h)
+    a.sum_duplicates()
+    d = a.shape[0]
+    if a.shape[0] != a.shape[1] or d < 2:
+        return None
+    pattern = (a != 0).astype(np.int8)
+    pattern = ((pattern + pattern.T) > 0).astype(np.int8).tocsr()
+    degree = np.diff(pattern.indptr)
+    is_global = degree > max(d // 2, max_block)
+    gi = np.nonzero(is_global)[0]
+    li = np.nonzero(~is_global)[0]
+    if len(li) < len(gi) or len(li) == 0:                    # mostly dense: not an arrow worth exploiting
+        return None
+    ncomp, labels = csgraph.connected_components(pattern[li][:, li], directed=False)
+    sizes = np.bincount(labels, minlength=ncomp)
+    M = int(sizes[0])
+    if ncomp < 2 or M > max_block or np.any(sizes != M):
+        return None
+    order = np.argsort(labels, kind='stable')                # component-major, indices ascending inside
+    sa = li[order].reshape(ncomp, M)
+    G, Dg = ncomp, len(gi)
+    perm = sa.reshape(-1)
+    loc = a[perm][:, perm].tocoo()
+    if np.any(loc.row // M != loc.col // M):
+        return None
+    blocks = np.zeros((G, M, M))
+    blocks[loc.row // M, loc.row % M, loc.col % M] = loc.data
+    cross = hgg = None
+    if Dg > 0:
+        cross = np.asarray(a[perm][:, gi].todense()).reshape(G, M, Dg)
+        hgg = np.asarray(a[gi][:, gi].todense())
+    return sa, gi, blocks, cross, hgg
+
+
 class BlockArrowHessian:
     """Device-resident block-arrow matrix of dimension ``d``.
 
@@ -34,6 +79,23 @@ class BlockArrowHessian:
         self.sparsity_array = sparsity_array      # torch int64 (G, M) on the device
         self.global_inds = global_inds            # torch int64 (Dg,)
         self.blocks, self.cross, self.hgg = blocks, cross, hgg
+
+    @classmethod
+    def from_sparse(cls, h, max_block=32, device=None):
+        """Recognise block-arrow structure in a scipy sparse matrix (e.g. the
+        ``coo_matrix`` the reference's ``SparseBlockHessian`` returns,
+        ``sparse_hessian_lib.py:107,162``) and move it to the GPU - SURVEY.md
+        section 8f item 3.  ``None`` when the pattern does not fit
+        (:func:`detect_block_arrow`); the caller then densifies."""
+        parts = detect_block_arrow(h, max_block=max_block)
+        if parts is None:
+            return None
+        sa, gi, blocks, cross, hgg = parts
+        dev = to_device(np.zeros(1), device).device
+        return cls(h.shape[0], torch.as_tensor(sa, dtype=torch.int64, device=dev),
+                   torch.as_tensor(gi, dtype=torch.int64, device=dev), blocks=to_device(blocks, dev),
+                   cross=None if cross is None else to_device(cross, dev),
+                   hgg=None if hgg is None else to_device(hgg, dev))
 
     def __add__(self, other):
         if not isinstance(other, BlockArrowHessian) or other.shape != self.shape:

@@ -61,8 +61,11 @@ def get_sparse_cholesky_solver(h):
         raise ValueError('`h` must be sparse.')
     arrow = BlockArrowHessian.from_sparse(h)
     if arrow is not None:
-        solve = arrow.get_solver()
-        solve.block_arrow = arrow
+        factorised = arrow.get_solver()
+
+        def solve(v):
+            return factorised(v)
+        solve.block_arrow = arrow      # (a bound method cannot carry attributes)
         return solve
     if h.shape[0] > 32768:
         raise ValueError('get_sparse_cholesky_solver: a general sparse matrix of dimension {} is too large to '

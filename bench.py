@@ -44,6 +44,7 @@ def parse():
     ap.add_argument('--e2e-steps', type=int, default=2)
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-tf32', action='store_true', help='skip the optional TF32 (tcgen05) rows')
     return ap.parse_args()
 
 
@@ -277,7 +278,38 @@ def main():
     G_cols = (X[idx] * st['resid'][idx, None]).T.contiguous()                # (D, 256)
     resid_check = ops.gemm(H, S[:, idx].contiguous().T.contiguous(), 'KC', 'KC') + G_cols
     rel_resid = float(torch.max(torch.abs(resid_check)) / torch.max(torch.abs(G_cols)))
+    S_cols64 = S[:, idx].clone()
     del S, G_cols, resid_check
+
+    # ---- optional reduced-precision rows: the same step with the two contractions on the
+    # tcgen05 TF32 engine (csrc/tgemm.cu).  Reported next to the FP64 headline, never instead of it.
+    tf32_rows = None
+    if not args.no_tf32:
+        tf32_rows = {}
+        for prec in ('tf32', 'tf32x3'):
+            try:
+                o32 = vt.objectives.GLMObjective(X, y, family='logistic', group=group, precision=prec)
+                t_step, sens32 = timed(lambda: vt.HyperparameterSensitivityLinearApproximation(o32, theta, w), reps)
+                tms = torch.tensor([t_step], dtype=torch.float64, device=dev)
+                if world > 1:
+                    dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+                t_step = float(tms.item())
+                S32 = sens32.get_dopt_dhyper()
+                err = float(torch.max(torch.abs(S32[:, idx] - S_cols64)) / torch.max(torch.abs(S_cols64)))
+                del sens32
+                t_sy, H32 = timed(lambda: ops.syrk_weighted(X, st['s'], precision=prec), reps)
+                t_ap, _ = timed(lambda: ops.ij_apply(hinv, X, st['resid'], out=S32, precision=prec), reps)
+                tf32_rows[prec] = {
+                    'value': N / (t_step * 1e-3), 'unit': UNIT, 'ms_per_step': t_step,
+                    'sampled_sens_err_vs_f64': err, 'tolerance': {'tf32': 5e-3, 'tf32x3': 2e-4}[prec],
+                    'ij_apply_ms': t_ap, 'ij_apply_tflops': 2.0 * D * D * n_loc / (t_ap * 1e-3) / 1e12,
+                    'syrk_ms': t_sy, 'syrk_tflops_algorithmic': float(D) * (D + 1) * n_loc / (t_sy * 1e-3) / 1e12,
+                    'engine': 'tcgen05.mma.kind::tf32, TMEM accumulators, TMA operands; statistics, Cholesky and '
+                              'inverse in FP64'}
+                del S32, H32, _, o32
+            except Exception as exc:          # report, never hide
+                tf32_rows[prec] = {'error': repr(exc)[:300]}
+    del S_cols64
 
     peaks = {}
     try:
@@ -348,6 +380,7 @@ def main():
             },
             'cpu_baseline': cpu_baseline,
             'e2e': e2e,
+            'optional_tf32_path': tf32_rows,
         }
         print(json.dumps(line))
     if world > 1:

@@ -116,6 +116,35 @@ int vt_potrs(const double* L, int64_t ldl, int D, const double* dinv, double* B,
 int vt_ij_apply(const double* Hinv, int64_t ldh, const double* X, int64_t ldx, int64_t N, int D,
                 const double* resid, double* S, int64_t lds, void* stream);
 
+/* ---- Optional reduced-precision path: TF32 on tcgen05 / TMEM / TMA -----------
+ * The north_star's "optional FP32/TF32 path" for the two contractions.  FP64
+ * (above) is the default and the only path the rtol 1e-8 parity bar applies to;
+ * these entry points are used only when the caller asks for precision 'tf32'
+ * (one TF32 product, ~1e-3 of the operand scale) or 'tf32x3' (three-term hi/lo
+ * split, ~1e-6).  split = 1 | 3 selects between them.
+ * vt_tf32_convert: hi = tf32(scale_r * x) stored as FP32 (+ lo = tf32 of the
+ *   remainder if lo != NULL); scale_r = rowscale[r] or sqrt(rowscale[r]);
+ *   ldo % 4 == 0, pad columns are zero-filled.
+ * vt_tf32_gemm: C (FP64) = alpha * rowscale[m] * colscale[n] * sum_k A(m,k) B(n,k)
+ *   on tcgen05.mma.kind::tf32 with FP32 accumulation in TMEM, flushed to FP64
+ *   every 4096 k; operand modes as for vt_dgemm (both operands the same mode).
+ * vt_ij_apply_tf32 / vt_syrk_tf32: the two hot contractions with FP64 inputs
+ *   and outputs; the observations are converted chunk by chunk inside.        */
+size_t vt_tf32_gemm_workspace_bytes(int M, int N, int64_t K, int split);
+int vt_tf32_convert(const double* X, int64_t ldx, int64_t rows, int cols, const double* rowscale, int sqrt_scale,
+                    float* hi, float* lo, int64_t ldo, void* stream);
+int vt_tf32_gemm(int M, int N, int64_t K, double alpha, const float* A_hi, const float* A_lo, int64_t lda, int amode,
+                 const float* B_hi, const float* B_lo, int64_t ldb, int bmode, double* C, int64_t ldc,
+                 const double* colscale, const double* rowscale, void* workspace, size_t workspace_bytes,
+                 void* stream);
+size_t vt_ij_apply_tf32_workspace_bytes(int64_t N, int D, int split);
+int vt_ij_apply_tf32(const double* Hinv, int64_t ldh, const double* X, int64_t ldx, int64_t N, int D,
+                     const double* resid, double* S, int64_t lds, int split, void* workspace,
+                     size_t workspace_bytes, void* stream);
+size_t vt_syrk_tf32_workspace_bytes(int64_t N, int D, int split);
+int vt_syrk_tf32(const double* X, int64_t ldx, int64_t N, int D, const double* s, double l2, double* H, int64_t ldh,
+                 int split, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- Prediction GEMV --------------------------------------------------------
  * y = alpha * A x + beta * y0 for row-major A (M x N), N long:
  * theta_hat + S (lam1 - lam0)   (sensitivity_lib.py:245-247).                */

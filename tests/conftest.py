@@ -13,6 +13,13 @@ GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+    # never test a stale library: rebuild in-tree when a source changed since the last build
+    try:
+        from vittles_b200 import build as vb
+        if not vb.is_current():
+            vb.build(verbose=False)
+    except Exception as exc:      # no nvcc: the tests that need the library will say so
+        sys.stderr.write('vittles_b200: could not (re)build the CUDA library: {}\n'.format(exc))
 
 
 @pytest.fixture(scope='session')

@@ -41,6 +41,13 @@ SIGNATURES = {
     'vt_potrf': (_I, [_P, _I64, _I, _P, _P, _P]),
     'vt_potrs': (_I, [_P, _I64, _I, _P, _P, _I64, _I, _P]),
     'vt_ij_apply': (_I, [_P, _I64, _P, _I64, _I64, _I, _P, _P, _I64, _P]),
+    'vt_tf32_gemm_workspace_bytes': (_SZ, [_I, _I, _I64, _I]),
+    'vt_tf32_convert': (_I, [_P, _I64, _I64, _I, _P, _I, _P, _P, _I64, _P]),
+    'vt_tf32_gemm': (_I, [_I, _I, _I64, _D, _P, _P, _I64, _I, _P, _P, _I64, _I, _P, _I64, _P, _P, _P, _SZ, _P]),
+    'vt_ij_apply_tf32_workspace_bytes': (_SZ, [_I64, _I, _I]),
+    'vt_ij_apply_tf32': (_I, [_P, _I64, _P, _I64, _I64, _I, _P, _P, _I64, _I, _P, _SZ, _P]),
+    'vt_syrk_tf32_workspace_bytes': (_SZ, [_I64, _I, _I]),
+    'vt_syrk_tf32': (_I, [_P, _I64, _I64, _I, _P, _D, _P, _I64, _I, _P, _SZ, _P]),
     'vt_gemv_workspace_bytes': (_SZ, [_I, _I64]),
     'vt_gemv': (_I, [_P, _I64, _I, _I64, _P, _D, _P, _D, _P, _P, _SZ, _P]),
     'vt_cg_init': (_I, [_I, _P, _P, _P, _P, _P]),

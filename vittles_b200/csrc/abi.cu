@@ -6,6 +6,7 @@
 #include "dgemm.cuh"
 #include "glm.cuh"
 #include "synth.cuh"
+#include "tgemm.cuh"
 
 namespace vt {
 const char* last_error();
@@ -184,6 +185,52 @@ int vt_ij_apply(const double* Hinv, int64_t ldh, const double* X, int64_t ldx, i
   p.colscale = resid;
   p.parts = 1;
   return gemm_launch(p, S(stream));
+}
+
+size_t vt_tf32_gemm_workspace_bytes(int M, int N, int64_t K, int split) { return tgemm_workspace_bytes(M, N, K, split); }
+
+int vt_tf32_convert(const double* X, int64_t ldx, int64_t rows, int cols, const double* rowscale, int sqrt_scale,
+                    float* hi, float* lo, int64_t ldo, void* stream) {
+  return tf32_convert(X, ldx, rows, cols, rowscale, sqrt_scale, hi, lo, ldo, S(stream));
+}
+
+int vt_tf32_gemm(int M, int N, int64_t K, double alpha, const float* A_hi, const float* A_lo, int64_t lda, int amode,
+                 const float* B_hi, const float* B_lo, int64_t ldb, int bmode, double* C, int64_t ldc,
+                 const double* colscale, const double* rowscale, void* workspace, size_t workspace_bytes,
+                 void* stream) {
+  VT_REQUIRE((amode == KC || amode == KS) && (bmode == KC || bmode == KS), "tf32_gemm: bad operand mode");
+  TGemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.A_hi = A_hi; p.A_lo = A_lo; p.lda = lda; p.amode = amode;
+  p.B_hi = B_hi; p.B_lo = B_lo; p.ldb = ldb; p.bmode = bmode;
+  p.C = C; p.ldc = ldc;
+  p.alpha = alpha;
+  p.colscale = colscale; p.rowscale = rowscale;
+  p.parts = 0;
+  p.workspace = static_cast<double*>(workspace);
+  p.workspace_bytes = workspace_bytes;
+  return tgemm_launch(p, S(stream));
+}
+
+size_t vt_ij_apply_tf32_workspace_bytes(int64_t N, int D, int split) { return ij_apply_tf32_workspace_bytes(N, D, split); }
+
+int vt_ij_apply_tf32(const double* Hinv, int64_t ldh, const double* X, int64_t ldx, int64_t N, int D,
+                     const double* resid, double* Sout, int64_t lds, int split, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  return ij_apply_tf32(Hinv, ldh, X, ldx, N, D, resid, Sout, lds, split, workspace, workspace_bytes, S(stream));
+}
+
+size_t vt_syrk_tf32_workspace_bytes(int64_t N, int D, int split) { return syrk_tf32_workspace_bytes(N, D, split); }
+
+int vt_syrk_tf32(const double* X, int64_t ldx, int64_t N, int D, const double* s, double l2, double* H, int64_t ldh,
+                 int split, void* workspace, size_t workspace_bytes, void* stream) {
+  int st = syrk_tf32(X, ldx, N, D, s, H, ldh, split, workspace, workspace_bytes, S(stream));
+  if (st != VT_OK) return st;
+  if (l2 != 0.0) {
+    add_diag_kernel<<<(D + 255) / 256, 256, 0, S(stream)>>>(H, ldh, D, l2);
+    VT_LAUNCH_CHECK();
+  }
+  return VT_OK;
 }
 
 size_t vt_gemv_workspace_bytes(int M, int64_t N) { return gemv_workspace_bytes(M, N); }

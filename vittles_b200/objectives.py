@@ -51,9 +51,18 @@ class GLMObjective(StructuredObjective):
 
         f(theta, w) = sum_n w_n [ b(x_n . theta) - y_n x_n . theta ] + l2/2 |theta|^2
 
-    ``family``: 'logistic' (b = softplus), 'poisson' (b = exp), 'gaussian'."""
+    ``family``: 'logistic' (b = softplus), 'poisson' (b = exp), 'gaussian'.
 
-    def __init__(self, X, y, family='logistic', l2=0.0, device=None, group=None, stream_chunks=16):
+    ``precision`` selects the engine of the two contractions (Hessian assembly
+    and the H^{-1} G^T apply): 'f64' (default; FP64 DMMA, the path the rtol 1e-8
+    parity bar applies to) or the optional 'tf32' / 'tf32x3' tcgen05 path
+    (relative error about 5e-4 / 2e-5 of the operand scale; statistics,
+    factorisation and the inverse stay in FP64)."""
+
+    def __init__(self, X, y, family='logistic', l2=0.0, device=None, group=None, stream_chunks=16,
+                 precision='f64'):
+        ops._split(precision)
+        self.precision = precision
         self._pending, self._host_src = [], None
         if (isinstance(X, torch.Tensor) and not X.is_cuda and X.dim() == 2 and X.dtype == torch.float64
                 and X.is_contiguous() and X.is_pinned() and X.shape[0] >= 64 * stream_chunks):
@@ -134,7 +143,7 @@ class GLMObjective(StructuredObjective):
             _, _, _, g = ops.glm_stats(self.X[r0:r1], theta, self.y[r0:r1], None if w is None else w[r0:r1],
                                        self.family, want_grad=True, out=(z[r0:r1], resid[r0:r1], s[r0:r1]))
             grad += g
-            ops.syrk_weighted(self.X[r0:r1], s[r0:r1], out=Hc)
+            ops.syrk_weighted(self.X[r0:r1], s[r0:r1], out=Hc, precision=self.precision)
             H += Hc
         self._allreduce(grad)
         self._allreduce(H)
@@ -173,7 +182,7 @@ class GLMObjective(StructuredObjective):
         if stats is None:
             stats = self.vt_stats(theta, w, want_grad=False)
         self._wait_resident()
-        H = ops.syrk_weighted(self.X, stats['s'], l2=0.0)
+        H = ops.syrk_weighted(self.X, stats['s'], l2=0.0, precision=self.precision)
         self._allreduce(H)
         if self.l2 != 0.0:
             H.diagonal().add_(self.l2)
@@ -182,7 +191,7 @@ class GLMObjective(StructuredObjective):
     def vt_ij_sensitivity(self, hinv, stats, out=None):
         """-H^{-1} G^T for this rank's observations, (D, N_local)."""
         self._wait_resident()
-        return ops.ij_apply(hinv, self.X, stats['resid'], out=out)
+        return ops.ij_apply(hinv, self.X, stats['resid'], out=out, precision=self.precision)
 
     def vt_hvp_fn(self, theta, w):
         """mat_times_vec for get_cg_solver: v -> H v, one fused pass over X."""

@@ -99,19 +99,77 @@ def gemm(A, B, amode='KC', bmode='KC', alpha=1.0, beta=0.0, out=None, M=None, N=
     return out
 
 
+# ------------------------------------------------- TF32 engine (optional) ----
+def tf32_convert(X, rowscale=None, sqrt_scale=False, split=1):
+    """(hi, lo | None): TF32-rounded FP32 copies of a float64 matrix, leading
+    dimension padded to a multiple of 4 (zero filled)."""
+    lib = _cabi.require_cuda()
+    _mat(X, 'X')
+    rows, cols = X.shape
+    ld = (cols + 3) // 4 * 4
+    hi = torch.empty((rows, ld), dtype=torch.float32, device=X.device)
+    lo = torch.empty_like(hi) if split == 3 else None
+    check(lib.vt_tf32_convert(ptr(X), _ld(X), rows, cols, ptr(rowscale), int(bool(sqrt_scale)), ptr(hi), ptr(lo), ld,
+                              stream()))
+    return hi, lo
+
+
+def tf32_gemm(A, B, amode='KC', bmode='KC', alpha=1.0, precision='tf32', colscale=None, rowscale=None, out=None):
+    """out (FP64) = alpha * rs[m] cs[n] sum_k A(m,k) B(n,k) on tcgen05.mma.kind::tf32
+    (FP32 accumulation in TMEM).  A and B are float64 CUDA matrices (KC: (rows, K);
+    KS: (K, rows)) that are rounded to TF32 (hi [+ lo]) here."""
+    lib = _cabi.require_cuda()
+    split = _split(precision)
+    if not split:
+        raise ValueError("tf32_gemm: precision must be 'tf32' or 'tf32x3'")
+    if amode != bmode:
+        raise ValueError('tf32_gemm: both operands must use the same mode')
+    mode = _cabi.OP_KC if amode == 'KC' else _cabi.OP_KS
+    Ah, Al = tf32_convert(A, split=split)
+    Bh, Bl = tf32_convert(B, split=split)
+    (M, K) = A.shape if mode == _cabi.OP_KC else A.shape[::-1]
+    (N, Kb) = B.shape if mode == _cabi.OP_KC else B.shape[::-1]
+    if K != Kb:
+        raise ValueError('tf32_gemm: inner dimensions differ ({} vs {})'.format(K, Kb))
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float64, device=A.device)
+    ws, wsb = _ws('tf32_gemm', lib.vt_tf32_gemm_workspace_bytes(M, N, K, split), A.device)
+    check(lib.vt_tf32_gemm(M, N, K, float(alpha), ptr(Ah), ptr(Al), Ah.stride(0), mode, ptr(Bh), ptr(Bl), Bh.stride(0),
+                           mode, ptr(out), _ld(out), ptr(colscale), ptr(rowscale), ptr(ws), wsb, stream()))
+    return out
+
+
 # ------------------------------------------------------- Hessian assembly ----
-def syrk_weighted(X, s=None, l2=0.0, out=None):
-    """H = X^T diag(s) X + l2 I  (FP64 DMMA, deterministic split-K)."""
+PRECISIONS = {'f64': 0, 'tf32': 1, 'tf32x3': 3}
+
+
+def _split(precision):
+    """0 for the FP64 DMMA engine, else the TF32 split (1 | 3) of the tcgen05 engine."""
+    if precision not in PRECISIONS:
+        raise ValueError("precision must be 'f64', 'tf32' or 'tf32x3', not {!r}".format(precision))
+    return PRECISIONS[precision]
+
+
+def syrk_weighted(X, s=None, l2=0.0, out=None, precision='f64'):
+    """H = X^T diag(s) X + l2 I  (FP64 DMMA, deterministic split-K; or the
+    optional TF32 / TF32x3 tcgen05 path, which needs s >= 0)."""
     lib = _cabi.require_cuda()
     _mat(X, 'X')
     N, D = X.shape
-    if s is None:
+    split = _split(precision)
+    if s is None and not split:
         s = torch.ones(N, dtype=torch.float64, device=X.device)
-    _f64(s, 's')
-    if s.numel() != N:
-        raise ValueError('s must have one entry per row of X')
+    if s is not None:
+        _f64(s, 's')
+        if s.numel() != N:
+            raise ValueError('s must have one entry per row of X')
     if out is None:
         out = torch.empty((D, D), dtype=torch.float64, device=X.device)
+    if split:
+        ws, wsb = _ws('syrk_tf32', lib.vt_syrk_tf32_workspace_bytes(N, D, split), X.device)
+        check(lib.vt_syrk_tf32(ptr(X), _ld(X), N, D, ptr(s), float(l2), ptr(out), _ld(out), split, ptr(ws), wsb,
+                               stream()))
+        return out
     wsb = lib.vt_syrk_workspace_bytes(N, D)
     ws, wsb = _ws('syrk', wsb, X.device)
     check(lib.vt_syrk_weighted(ptr(X), _ld(X), N, D, ptr(s), float(l2), ptr(out), _ld(out), ptr(ws), wsb, stream()))
@@ -229,14 +287,21 @@ def potrf(H, overwrite=False, check_pd=True):
 
 
 # ------------------------------------------------------------- IJ apply ----
-def ij_apply(Hinv, X, resid, out=None):
+def ij_apply(Hinv, X, resid, out=None, precision='f64'):
     """S (D, N) = -Hinv @ (resid[:, None] * X).T without materialising the
-    cross-Hessian."""
+    cross-Hessian.  ``precision``: 'f64' (DMMA engine, the default) or the
+    optional 'tf32' / 'tf32x3' tcgen05 path."""
     lib = _cabi.require_cuda()
     _mat(Hinv, 'Hinv'); _mat(X, 'X')
     N, D = X.shape
     if out is None:
         out = torch.empty((D, N), dtype=torch.float64, device=X.device)
+    split = _split(precision)
+    if split:
+        ws, wsb = _ws('ij_tf32', lib.vt_ij_apply_tf32_workspace_bytes(N, D, split), X.device)
+        check(lib.vt_ij_apply_tf32(ptr(Hinv), _ld(Hinv), ptr(X), _ld(X), N, D, ptr(_f64(resid, 'resid')), ptr(out),
+                                   _ld(out), split, ptr(ws), wsb, stream()))
+        return out
     check(lib.vt_ij_apply(ptr(Hinv), _ld(Hinv), ptr(X), _ld(X), N, D, ptr(_f64(resid, 'resid')), ptr(out), _ld(out),
                           stream()))
     return out

@@ -145,6 +145,27 @@ size_t vt_syrk_tf32_workspace_bytes(int64_t N, int D, int split);
 int vt_syrk_tf32(const double* X, int64_t ldx, int64_t N, int D, const double* s, double l2, double* H, int64_t ldh,
                  int split, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- FP64-grade contraction on the INT8 tensor cores (error-free slicing) ------
+ * An additional engine for the H^{-1} G^T apply (precision 'f64_ozaki'): every
+ * row of both operands is scaled by a power of two and cut into `nslices`
+ * (6..8) signed 7-bit digits (vt_ozaki_slice: out[s][r][k] int8, scale_out[r] =
+ * 2^e_r * fold[r]); the nslices (nslices + 1) / 2 significant digit products
+ * run exactly on tcgen05.mma.kind::i8 with INT32 accumulators in TMEM and are
+ * recombined in INT64 / FP64 in the epilogue (vt_ozaki_gemm, K <= 16384).  With
+ * 7 slices the result is within ~1e-11 of sigma_m tau_n (the row scales), i.e.
+ * inside the rtol 1e-8 parity bar of the FP64 path; 8 slices give ~1e-13.
+ * vt_ij_apply_ozaki is vt_ij_apply on this engine (observations sliced chunk by
+ * chunk inside).                                                               */
+int vt_ozaki_slice(const double* X, int64_t ldx, int64_t rows, int cols, int8_t* out, int64_t ldo, int64_t slice_stride,
+                   int nslices, double* scale_out, const double* fold, void* stream);
+int vt_ozaki_gemm(int M, int N, int K, const int8_t* A, int64_t lda, int64_t a_slice_stride, const int8_t* B,
+                  int64_t ldb, int64_t b_slice_stride, int nslices, double alpha, const double* rowscale,
+                  const double* colscale, double* C, int64_t ldc, void* stream);
+size_t vt_ij_apply_ozaki_workspace_bytes(int64_t N, int D, int nslices);
+int vt_ij_apply_ozaki(const double* Hinv, int64_t ldh, const double* X, int64_t ldx, int64_t N, int D,
+                      const double* resid, double* S, int64_t lds, int nslices, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
 /* ---- Prediction GEMV --------------------------------------------------------
  * y = alpha * A x + beta * y0 for row-major A (M x N), N long:
  * theta_hat + S (lam1 - lam0)   (sensitivity_lib.py:245-247).                */

@@ -1,0 +1,105 @@
+"""GPU tests of the INT8 error-free-slicing engine (``csrc/ogemm.cu``): FP64-grade
+results from tcgen05.mma.kind::i8.  Unlike the TF32 path this engine IS held to
+the parity bar of the FP64 path (rtol 1e-8 with the 1e-12 max|ref| floor of
+``conftest.assert_close``): the slicing is exact, every digit product is exact in
+INT32, and only digit pairs below 2^-56 of the row scales are dropped."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def vt():
+    import vittles_b200
+    return vittles_b200
+
+
+def _rnd(*shape, seed=0):
+    g = torch.Generator(device='cuda').manual_seed(seed)
+    return torch.randn(*shape, device='cuda', dtype=torch.float64, generator=g)
+
+
+@pytest.mark.parametrize('S', [7, 8])
+def test_slicing_is_exact_to_7S_bits(vt, S):
+    X = _rnd(300, 102) * torch.exp(3 * _rnd(300, 1, seed=1))        # rows of very different magnitude
+    X[7] = 0.0                                                      # an all-zero row
+    d, sc = vt.ops.ozaki_slice(X, S)
+    assert d.dtype == torch.int8 and d.shape == (S, 300, 112)
+    assert int(d.abs().max()) <= 127 and bool((d[:, :, 102:] == 0).all())
+    assert bool((torch.frexp(sc)[0] == 0.5).all())                  # powers of two
+    rowmax = X.abs().max(dim=1).values
+    assert bool((sc > rowmax).all())
+    rec = sum(d[s, :, :102].double() * 2.0 ** (-7 * (s + 1)) for s in range(S)) * sc[:, None]
+    resid = (X - rec).abs().max(dim=1).values
+    assert bool((resid <= sc * 2.0 ** (-7 * S)).all())              # truncation: less than one unit of the last digit
+    fold = _rnd(300, seed=2)
+    _, sc2 = vt.ops.ozaki_slice(X, S, fold=fold)
+    assert torch.equal(sc2, sc * fold)
+
+
+@pytest.mark.parametrize('shape', [(128, 64, 128), (1024, 1024, 1024), (200, 300, 100), (130, 515, 1000), (1, 1, 1),
+                                   (257, 65, 36)])
+def test_ozaki_gemm_is_fp64_grade(vt, shape):
+    M, N, K = shape
+    A, B = _rnd(M, K, seed=3), _rnd(N, K, seed=4)
+    out = vt.ops.ozaki_gemm(A, B, alpha=-2.0)
+    assert_close(out, -2.0 * (A @ B.T), rtol=1e-8, atol_scale=1e-12, what='ozaki_gemm {}'.format(shape))
+    out8 = vt.ops.ozaki_gemm(A, B, alpha=-2.0, nslices=8)
+    assert float((out8 + 2.0 * (A @ B.T)).abs().max() / (A @ B.T).abs().max()) < 1e-12
+
+
+def test_ozaki_gemm_badly_scaled_rows(vt):
+    """Row scales spanning 12 orders of magnitude: the per-row power-of-two scaling keeps every row at 49 bits."""
+    A = _rnd(256, 512, seed=5) * torch.exp(6 * _rnd(256, 1, seed=6))
+    B = _rnd(192, 512, seed=7) * torch.exp(6 * _rnd(192, 1, seed=8))
+    out = vt.ops.ozaki_gemm(A, B)
+    ref = A @ B.T
+    rowcol = A.abs().max(dim=1).values[:, None] * B.abs().max(dim=1).values[None, :]
+    assert float(((out - ref).abs() / rowcol).max()) < 1e-10
+
+
+def test_ij_apply_on_the_int8_engine(vt):
+    N, D = 40000, 1024
+    X = vt.ops.synth_design(11, 0, N, D, 'cuda')
+    Hm = _rnd(D, D, seed=9)
+    Hinv = torch.linalg.inv(Hm @ Hm.T / D + 0.05 * torch.eye(D, device='cuda', dtype=torch.float64)).contiguous()
+    resid = _rnd(N, seed=10)
+    S64 = vt.ops.ij_apply(Hinv, X, resid)
+    S = vt.ops.ij_apply(Hinv, X, resid, precision='f64_ozaki')
+    assert_close(S, S64, rtol=1e-8, atol_scale=1e-12, what='ij_apply f64_ozaki')
+    # ragged sizes
+    N2, D2 = 3001, 77
+    X2 = vt.ops.synth_design(12, 0, N2, D2, 'cuda')
+    Hinv2 = torch.eye(D2, device='cuda', dtype=torch.float64) + 0.1 * _rnd(D2, D2, seed=11)
+    r2 = _rnd(N2, seed=12)
+    assert_close(vt.ops.ij_apply(Hinv2, X2, r2, precision='f64_ozaki'), vt.ops.ij_apply(Hinv2, X2, r2), rtol=1e-8,
+                 atol_scale=1e-12)
+
+
+def test_ij_sensitivities_through_the_api_match_the_oracle(vt):
+    """precision='f64_ozaki' through HyperparameterSensitivityLinearApproximation: the
+    same rtol 1e-8 bar against the oracle as the default FP64 path."""
+    from oracle import models, sensitivity as osens
+    n, d = 4000, 64
+    X, y, _ = models.synth_logistic(31, n, d)
+    w = np.ones(n)
+    theta = models.glm_newton(X, y, w)
+    ref = osens.linear_sensitivity(models.glm_objective(X, y), theta, w)
+    obj = vt.objectives.GLMObjective(X, y, family='logistic', precision='f64_ozaki')
+    sens = vt.HyperparameterSensitivityLinearApproximation(obj, theta, w)
+    assert_close(sens.get_dopt_dhyper(), ref['sens'], rtol=1e-8, atol_scale=1e-12, what='dopt_dhyper (f64_ozaki)')
+    assert_close(sens.get_hessian_at_opt(), ref['hessian'], rtol=1e-10)
+
+
+def test_bad_arguments(vt):
+    A = _rnd(8, 20000)
+    with pytest.raises(ValueError):
+        vt.ops.ozaki_gemm(A, A)                       # K beyond the INT32 accumulation bound
+    with pytest.raises(ValueError):
+        vt.ops.ozaki_gemm(_rnd(8, 16), _rnd(8, 32))
+    with pytest.raises(ValueError):
+        vt.ops.ozaki_gemm(_rnd(8, 16), _rnd(8, 16), nslices=3)

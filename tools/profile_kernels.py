@@ -33,5 +33,11 @@ for _ in range(REPS):
 delta = torch.rand(N, device=dev, dtype=torch.float64)
 for _ in range(REPS):
     p = ops.gemv(S, delta)
+# optional TF32 path (tcgen05): two conversion chunks of the apply and of the Hessian assembly
+NT = min(N, 2 * 37888)
+S32 = H32 = None
+for prec in ('tf32', 'tf32x3'):
+    S32 = ops.ij_apply(hinv, X[:NT], resid[:NT], precision=prec)
+    H32 = ops.syrk_weighted(X[:NT], s[:NT].abs(), precision=prec)
 torch.cuda.synchronize()
 print('profile run done', float(H[0, 0]), float(q[0]), float(dd[0]), float(p[0]))

@@ -7,6 +7,7 @@
 #include "glm.cuh"
 #include "synth.cuh"
 #include "tgemm.cuh"
+#include "ogemm.cuh"
 
 namespace vt {
 const char* last_error();
@@ -231,6 +232,28 @@ int vt_syrk_tf32(const double* X, int64_t ldx, int64_t N, int D, const double* s
     VT_LAUNCH_CHECK();
   }
   return VT_OK;
+}
+
+int vt_ozaki_slice(const double* X, int64_t ldx, int64_t rows, int cols, int8_t* out, int64_t ldo, int64_t slice_stride,
+                   int nslices, double* scale_out, const double* fold, void* stream) {
+  return ozaki_slice(X, ldx, rows, cols, out, ldo, slice_stride, nslices, scale_out, fold, S(stream));
+}
+
+int vt_ozaki_gemm(int M, int N, int K, const int8_t* A, int64_t lda, int64_t a_slice_stride, const int8_t* B,
+                  int64_t ldb, int64_t b_slice_stride, int nslices, double alpha, const double* rowscale,
+                  const double* colscale, double* C, int64_t ldc, void* stream) {
+  return ogemm_launch(M, N, K, A, lda, a_slice_stride, B, ldb, b_slice_stride, nslices, alpha, rowscale, colscale, C, ldc,
+                      S(stream));
+}
+
+size_t vt_ij_apply_ozaki_workspace_bytes(int64_t N, int D, int nslices) {
+  return ij_apply_ozaki_workspace_bytes(N, D, nslices);
+}
+
+int vt_ij_apply_ozaki(const double* Hinv, int64_t ldh, const double* X, int64_t ldx, int64_t N, int D,
+                      const double* resid, double* Sout, int64_t lds, int nslices, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  return ij_apply_ozaki(Hinv, ldh, X, ldx, N, D, resid, Sout, lds, nslices, workspace, workspace_bytes, S(stream));
 }
 
 size_t vt_gemv_workspace_bytes(int M, int64_t N) { return gemv_workspace_bytes(M, N); }

@@ -1,0 +1,389 @@
+// FP64-grade GEMM on the INT8 tensor cores by error-free slicing - see ogemm.cuh.
+#include "ogemm.cuh"
+#include "tc05.cuh"
+
+namespace vt {
+
+using namespace tc05;
+
+namespace {
+
+constexpr int OBM = 128;               // tile rows (TMEM lanes)
+constexpr int OBN = 64;                // tile columns: S accumulators x 64 columns <= 512 TMEM columns
+constexpr int OBK = 128;               // int8 elements (bytes) per k-block = one 128-byte swizzle row
+constexpr int O_UMMA_K = 32;           // k per tcgen05.mma.kind::i8
+constexpr int O_THREADS = 192;         // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int A_TILE_BYTES = OBM * OBK;        // 16 KB: one slice of the A tile for one k-block
+constexpr int B_TILE_BYTES = OBN * OBK;        //  8 KB: one slice of the B tile for one k-block
+constexpr int A_RING = 4;                      // A slices stream through a 4-deep ring
+constexpr int B_BUFS = 2;                      // all S slices of the B tile, double buffered over k-blocks
+
+template <int S>
+struct OCfg {
+  static constexpr int B_BUF_BYTES = S * B_TILE_BYTES;
+  static constexpr int SMEM_BYTES = B_BUFS * B_BUF_BYTES + A_RING * A_TILE_BYTES + 1024 + 256;
+};
+
+struct OKernelArgs {
+  int M, N, kblocks, tiles_m;
+  long ntiles;
+  double* C; long ldc;
+  double alpha;
+  const double* rowscale;
+  const double* colscale;
+  int c_vec;
+};
+
+// One CTA per SM walks output tiles (row blocks fastest, so that the CTAs running
+// together share the B slices in L2).  Per k-block the S slices of the B tile are
+// loaded once (one 3-D TMA box) and the slices of the A tile stream through a
+// ring; slice s of A meets slices t = 0 .. S-1-s of B, and product (s, t) goes to
+// accumulator s + t.  Every INT8 tile loaded is used by (S+1)/2 products on
+// average, which keeps the L2 -> shared-memory traffic at ~47 B/clk/SM at the
+// tensor peak.
+template <int S>
+__global__ void __launch_bounds__(O_THREADS, 1)
+ogemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const OKernelArgs a) {
+  constexpr int B_BUF_BYTES = OCfg<S>::B_BUF_BYTES;
+  extern __shared__ uint8_t og_smem_raw[];
+  const uint32_t smem_base = (smem_u32(og_smem_raw) + 1023u) & ~1023u;
+  const uint32_t sB0 = smem_base;                                   // B_BUFS x [S][64][128 B]
+  const uint32_t sA0 = smem_base + B_BUFS * B_BUF_BYTES;            // A_RING x [128][128 B]
+  const uint32_t bar_base = sA0 + A_RING * A_TILE_BYTES;
+  auto bfull = [&](int i) { return bar_base + 8u * i; };
+  auto bempty = [&](int i) { return bar_base + 8u * (B_BUFS + i); };
+  auto afull = [&](int i) { return bar_base + 8u * (2 * B_BUFS + i); };
+  auto aempty = [&](int i) { return bar_base + 8u * (2 * B_BUFS + A_RING + i); };
+  const uint32_t tfull = bar_base + 8u * (2 * B_BUFS + 2 * A_RING);
+  const uint32_t tempty = tfull + 8u;
+  const uint32_t tmem_slot = tempty + 8u;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(og_smem_raw + (tmem_slot - smem_u32(og_smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+    for (int i = 0; i < B_BUFS; ++i) { mbar_init_(bfull(i), 1); mbar_init_(bempty(i), 1); }
+    for (int i = 0; i < A_RING; ++i) { mbar_init_(afull(i), 1); mbar_init_(aempty(i), 1); }
+    mbar_init_(tfull, 1);
+    mbar_init_(tempty, 4);
+    fence_barrier_init_();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ================================================== TMA producer ====
+    if (elect_one()) {
+      int bs = 0, as = 0;
+      uint32_t bph = 0, aph = 0;
+      for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        const int m0 = (int)(tile % a.tiles_m) * OBM, n0 = (int)(tile / a.tiles_m) * OBN;
+        for (int kb = 0; kb < a.kblocks; ++kb) {
+          mbar_wait_(bempty(bs), bph ^ 1u);
+          mbar_arrive_expect_tx_(bfull(bs), (uint32_t)B_BUF_BYTES);
+          tma_load_3d(sB0 + bs * B_BUF_BYTES, &mapB, bfull(bs), kb * OBK, n0, 0);        // box {128 B, 64 rows, S slices}
+          if (++bs == B_BUFS) { bs = 0; bph ^= 1u; }
+#pragma unroll 1
+          for (int s = 0; s < S; ++s) {
+            mbar_wait_(aempty(as), aph ^ 1u);
+            mbar_arrive_expect_tx_(afull(as), (uint32_t)A_TILE_BYTES);
+            tma_load_3d(sA0 + as * A_TILE_BYTES, &mapA, afull(as), kb * OBK, m0, s);     // box {128 B, 128 rows, 1 slice}
+            if (++as == A_RING) { as = 0; aph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ==================================================== MMA issuer ====
+    if (elect_one()) {
+      // instruction descriptor: D = S32, A = B = signed INT8, both K-major, N >> 3, M >> 4
+      constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OBN >> 3) << 17) |
+                                 ((uint32_t)(OBM >> 4) << 24);
+      // K-major 128-byte-swizzled operand: descriptor hi half = SBO 1024 B | version 1 | SWIZZLE_128B (constant),
+      // lo half = (address >> 4) | LBO 16 B << 16; one UMMA_K = 32 B = +2, one B slice = 8 KB = +512.
+      const uint64_t d0 = umma_desc(0u, 16u, 1024u, 2u);
+      const uint32_t desc_hi = (uint32_t)(d0 >> 32), desc_lo0 = (uint32_t)d0;
+      int bs = 0, as = 0;
+      uint32_t bph = 0, aph = 0, tph = 0;
+      for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        mbar_wait_(tempty, tph ^ 1u);          // the epilogue has drained the accumulators of the previous tile
+        tc_fence_after();
+        for (int kb = 0; kb < a.kblocks; ++kb) {
+          mbar_wait_(bfull(bs), bph);
+          const uint32_t b_lo0 = desc_lo0 + ((sB0 + bs * B_BUF_BYTES) >> 4);
+          const uint32_t first = kb == 0 ? 0u : 1u;
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            mbar_wait_(afull(as), aph);
+            tc_fence_after();
+            const uint32_t a_lo0 = desc_lo0 + ((sA0 + as * A_TILE_BYTES) >> 4);
+#pragma unroll
+            for (int t = 0; t < S - s; ++t) {
+              const uint32_t tmem_d = tmem_base + (uint32_t)((s + t) * OBN);
+#pragma unroll
+              for (int kk = 0; kk < OBK / O_UMMA_K; ++kk)
+                umma_i8_lohi(tmem_d, a_lo0 + 2u * kk, desc_hi, b_lo0 + (uint32_t)(t * (B_TILE_BYTES >> 4)) + 2u * kk, desc_hi,
+                             idesc, (s == 0 && kk == 0) ? first : 1u);
+            }
+            umma_commit(aempty(as));
+            if (++as == A_RING) { as = 0; aph ^= 1u; }
+          }
+          umma_commit(bempty(bs));
+          if (++bs == B_BUFS) { bs = 0; bph ^= 1u; }
+        }
+        umma_commit(tfull);
+        tph ^= 1u;
+      }
+    }
+  } else {
+    // ====================================================== epilogue ====
+    const int quarter = warp & 3;
+    const int row_local = quarter * 32 + lane;
+    uint32_t tph = 0;
+    const double w_hi = 1.0 / 268435456.0;                        // 2^-28: accumulators 0..2 combined as P0 2^14 + P1 2^7 + P2
+    const double w_lo = exp2(-7.0 * (double)(S + 1));             // accumulators 3..S-1 combined with P_{S-1} at weight 1
+    for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+      const int m0 = (int)(tile % a.tiles_m) * OBM, n0 = (int)(tile / a.tiles_m) * OBN;
+      const int grow = m0 + row_local;
+      mbar_wait_(tfull, tph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+      const double rs = (grow < a.M) ? a.alpha * (a.rowscale ? a.rowscale[grow] : 1.0) : 0.0;
+#pragma unroll 1
+      for (int c = 0; c < OBN; c += 16) {
+        long long hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) hi[j] = lo[j] = 0;
+#pragma unroll
+        for (int g = 0; g < S; ++g) {
+          uint32_t v[16];
+          tmem_ld16(taddr + (uint32_t)(g * OBN + c), v);
+          tmem_wait_ld();
+          if (g < 3) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) hi[j] = hi[j] * 128 + (long long)(int)v[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) lo[j] = lo[j] * 128 + (long long)(int)v[j];
+          }
+        }
+        if (grow < a.M) {
+          const int gcol = n0 + c;
+          double out[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const double cs = (a.colscale && gcol + j < a.N) ? a.colscale[gcol + j] : 1.0;
+            out[j] = rs * cs * fma((double)lo[j], w_lo, (double)hi[j] * w_hi);
+          }
+          double* cp = a.C + (long)grow * a.ldc + gcol;
+          if (a.c_vec && gcol + 16 <= a.N) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) st_global_v4(cp + j, out[j], out[j + 1], out[j + 2], out[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (gcol + j < a.N) cp[j] = out[j];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_(tempty);
+      tph ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// One warp per row: row maximum -> power-of-two scale -> S truncated base-128 digits.
+// Every operation is exact in FP64 (scaling by powers of two, truncation, subtraction
+// of the truncated part), so sum_s d_s 2^{-7s} reproduces x / sigma to 7 S bits.
+__global__ void __launch_bounds__(256) ozaki_slice_kernel(const double* __restrict__ X, long ldx, long rows, int cols,
+                                                          int8_t* __restrict__ out, long ldo, long slice_stride,
+                                                          int nslices, double* __restrict__ scale_out,
+                                                          const double* __restrict__ fold) {
+  const int lane = threadIdx.x & 31;
+  const long warp0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  for (long r = warp0; r < rows; r += nwarps) {
+    const double* xr = X + r * ldx;
+    double m = 0.0;
+    for (int c = lane; c < cols; c += 32) m = fmax(m, fabs(xr[c]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    int e = 0;
+    if (m > 0.0) (void)frexp(m, &e);                   // m = f 2^e, f in [0.5, 1)  ->  |x| 2^-e < 1
+    const double inv = ldexp(1.0, -e);
+    if (lane == 0) scale_out[r] = ldexp(1.0, e) * (fold ? fold[r] : 1.0);
+    // four consecutive elements per lane: one 4-byte store per slice, 128 contiguous bytes per warp
+    for (int c0 = lane * 4; c0 < ldo; c0 += 128) {
+      double y[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) y[j] = (c0 + j < cols) ? xr[c0 + j] * inv : 0.0;
+      for (int s = 0; s < nslices; ++s) {
+        uint32_t packed = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          y[j] *= 128.0;
+          const int d = __double2int_rz(y[j]);
+          y[j] -= (double)d;
+          packed |= ((uint32_t)d & 0xFFu) << (8 * j);
+        }
+        *reinterpret_cast<uint32_t*>(out + (long)s * slice_stride + r * ldo + c0) = packed;
+      }
+    }
+  }
+}
+
+// 3-D uint8 tensor map over the slices: dims {K, rows, S}, box {128, box_rows, box_slices}, 128-byte swizzle.
+int make_slice_map(CUtensorMap* map, const int8_t* base, long rows, int K, long ld, long slice_stride, int nslices,
+                   int box_rows, int box_slices) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc) {
+    set_error("ogemm: cuTensorMapEncodeTiled is not available from this driver");
+    return VT_ERR_CUDA;
+  }
+  cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)nslices};
+  cuuint64_t gstride[2] = {(cuuint64_t)ld, (cuuint64_t)slice_stride};
+  cuuint32_t box[3] = {(cuuint32_t)OBK, (cuuint32_t)box_rows, (cuuint32_t)box_slices};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(base), gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("ogemm: cuTensorMapEncodeTiled failed with code %d (rows=%ld K=%d ld=%ld slice_stride=%ld)", (int)r, rows,
+              K, ld, slice_stride);
+    return VT_ERR_CUDA;
+  }
+  return VT_OK;
+}
+
+template <int S>
+int launch_s(const CUtensorMap& mA, const CUtensorMap& mB, const OKernelArgs& a, cudaStream_t stream) {
+  auto kern = ogemm_kernel<S>;
+  VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, OCfg<S>::SMEM_BYTES));
+  const long slots = num_sms();
+  const int grid = (int)(a.ntiles < slots ? a.ntiles : slots);
+  kern<<<grid, O_THREADS, OCfg<S>::SMEM_BYTES, stream>>>(mA, mB, a);
+  VT_LAUNCH_CHECK();
+  return VT_OK;
+}
+
+inline size_t align_up(size_t x, size_t al) { return (x + al - 1) / al * al; }
+
+long ozaki_chunk_rows(long N, int D, int nslices) {
+  const long ld = (D + 15) / 16 * 16;
+  const size_t budget = (size_t)288 << 20;                 // all slices of one chunk
+  long nb = (long)(budget / ((size_t)ld * nslices)) / OBN;
+  if (nb < 1) nb = 1;
+  // tiles_m * nb output tiles should fill whole waves of the persistent grid
+  const int G = num_sms(), tiles_m = (D + OBM - 1) / OBM;
+  long best = nb;
+  double best_eff = 0.0;
+  for (long b = nb; b >= 1 && b > nb / 2; --b) {
+    const long T = b * tiles_m;
+    const double eff = (double)T / ((double)G * (double)((T + G - 1) / G));
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = b; }
+  }
+  long rows = best * OBN;
+  if (rows > N) rows = N;
+  return rows;
+}
+
+}  // namespace
+
+int ozaki_slice(const double* X, long ldx, long rows, int cols, int8_t* out, long ldo, long slice_stride, int nslices,
+                double* scale_out, const double* fold, cudaStream_t stream) {
+  VT_REQUIRE(X && out && scale_out, "ozaki_slice: null pointer");
+  VT_REQUIRE(rows >= 0 && cols >= 1 && ldx >= cols && ldo >= cols && ldo % 16 == 0, "ozaki_slice: bad shape");
+  VT_REQUIRE(nslices >= 1 && nslices <= OZAKI_MAX_SLICES && slice_stride >= rows * ldo && slice_stride % 16 == 0,
+             "ozaki_slice: bad slice layout");
+  VT_REQUIRE(reinterpret_cast<uintptr_t>(out) % 16 == 0, "ozaki_slice: output must be 16-byte aligned");
+  if (rows == 0) return VT_OK;
+  long blocks = (rows + 7) / 8;
+  const long cap = (long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  ozaki_slice_kernel<<<(unsigned)blocks, 256, 0, stream>>>(X, ldx, rows, cols, out, ldo, slice_stride, nslices, scale_out,
+                                                          fold);
+  VT_LAUNCH_CHECK();
+  return VT_OK;
+}
+
+int ogemm_launch(int M, int N, int K, const int8_t* A, long lda, long a_slice_stride, const int8_t* B, long ldb,
+                 long b_slice_stride, int nslices, double alpha, const double* rowscale, const double* colscale, double* C,
+                 long ldc, cudaStream_t stream) {
+  VT_REQUIRE(M >= 0 && N >= 0 && K >= 1, "ogemm: bad dimensions");
+  if (M == 0 || N == 0) return VT_OK;
+  VT_REQUIRE(A && B && C, "ogemm: null operand");
+  VT_REQUIRE(nslices >= 6 && nslices <= OZAKI_MAX_SLICES, "ogemm: 6, 7 or 8 slices are instantiated");
+  VT_REQUIRE(K <= OZAKI_MAX_K, "ogemm: K = %d exceeds %d (INT32 accumulation bound)", K, OZAKI_MAX_K);
+  VT_REQUIRE(lda % 16 == 0 && ldb % 16 == 0 && a_slice_stride % 16 == 0 && b_slice_stride % 16 == 0,
+             "ogemm: pitches must be multiples of 16 bytes");
+  VT_REQUIRE(reinterpret_cast<uintptr_t>(A) % 16 == 0 && reinterpret_cast<uintptr_t>(B) % 16 == 0,
+             "ogemm: operands must be 16-byte aligned");
+  CUtensorMap mA, mB;
+  int st = make_slice_map(&mA, A, M, K, lda, a_slice_stride, nslices, OBM, 1);
+  if (st != VT_OK) return st;
+  st = make_slice_map(&mB, B, N, K, ldb, b_slice_stride, nslices, OBN, nslices);
+  if (st != VT_OK) return st;
+  OKernelArgs a{};
+  a.M = M; a.N = N;
+  a.kblocks = (K + OBK - 1) / OBK;
+  a.tiles_m = (M + OBM - 1) / OBM;
+  a.ntiles = (long)a.tiles_m * ((N + OBN - 1) / OBN);
+  a.C = C; a.ldc = ldc;
+  a.alpha = alpha;
+  a.rowscale = rowscale; a.colscale = colscale;
+  a.c_vec = (ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(C) % 32 == 0);
+  switch (nslices) {
+    case 6: return launch_s<6>(mA, mB, a, stream);
+    case 7: return launch_s<7>(mA, mB, a, stream);
+    default: return launch_s<8>(mA, mB, a, stream);
+  }
+}
+
+size_t ij_apply_ozaki_workspace_bytes(long N, int D, int nslices) {
+  const long ld = (D + 15) / 16 * 16;
+  const long ch = ozaki_chunk_rows(N, D, nslices);
+  return align_up((size_t)nslices * D * ld, 256) + align_up((size_t)D * 8, 256) +
+         align_up((size_t)nslices * ch * ld, 256) + align_up((size_t)ch * 8, 256);
+}
+
+int ij_apply_ozaki(const double* Hinv, long ldh, const double* X, long ldx, long N, int D, const double* resid,
+                   double* S, long lds, int nslices, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  VT_REQUIRE(Hinv && X && resid && S && workspace, "ij_apply_ozaki: null pointer");
+  VT_REQUIRE(D >= 1 && D <= OZAKI_MAX_K && N >= 0 && ldh >= D && ldx >= D && lds >= N, "ij_apply_ozaki: bad shape");
+  VT_REQUIRE(nslices >= 6 && nslices <= OZAKI_MAX_SLICES, "ij_apply_ozaki: 6, 7 or 8 slices");
+  VT_REQUIRE(workspace_bytes >= ij_apply_ozaki_workspace_bytes(N, D, nslices), "ij_apply_ozaki: workspace too small");
+  if (N == 0) return VT_OK;
+  const long ld = (D + 15) / 16 * 16;
+  const long ch = ozaki_chunk_rows(N, D, nslices);
+  char* w = static_cast<char*>(workspace);
+  int8_t* As = reinterpret_cast<int8_t*>(w);
+  w += align_up((size_t)nslices * D * ld, 256);
+  double* sigma = reinterpret_cast<double*>(w);
+  w += align_up((size_t)D * 8, 256);
+  int8_t* Bs = reinterpret_cast<int8_t*>(w);
+  w += align_up((size_t)nslices * ch * ld, 256);
+  double* tau = reinterpret_cast<double*>(w);
+  int st = ozaki_slice(Hinv, ldh, D, D, As, ld, (long)D * ld, nslices, sigma, nullptr, stream);
+  if (st != VT_OK) return st;
+  for (long r0 = 0; r0 < N; r0 += ch) {
+    const long rows = (N - r0 < ch) ? N - r0 : ch;
+    st = ozaki_slice(X + r0 * ldx, ldx, rows, D, Bs, ld, ch * ld, nslices, tau, resid + r0, stream);   // tau_n * resid_n
+    if (st != VT_OK) return st;
+    st = ogemm_launch(D, (int)rows, D, As, ld, (long)D * ld, Bs, ld, ch * ld, nslices, -1.0, sigma, tau, S + r0, lds,
+                      stream);
+    if (st != VT_OK) return st;
+  }
+  return VT_OK;
+}
+
+}  // namespace vt

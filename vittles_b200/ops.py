@@ -13,6 +13,7 @@ from . import _cabi
 from ._cabi import check, ptr, stream
 
 _workspaces = {}
+OZAKI_SLICES = 7      # digits per operand of the 'f64_ozaki' engine (49 bits; 8 -> 56 bits)
 
 
 def _ws(key, nbytes, device):
@@ -139,8 +140,40 @@ def tf32_gemm(A, B, amode='KC', bmode='KC', alpha=1.0, precision='tf32', colscal
     return out
 
 
+# ------------------------------------- INT8 error-free slicing (optional) ----
+def ozaki_slice(X, nslices=OZAKI_SLICES, fold=None):
+    """(digits (nslices, rows, ld) int8, scale (rows,) float64) of a float64 matrix:
+    X[r, k] = scale[r] * sum_s digits[s, r, k] 2^{-7 (s + 1)} up to 2^{-7 nslices}
+    (``fold`` multiplies the returned scale row by row)."""
+    lib = _cabi.require_cuda()
+    _mat(X, 'X')
+    rows, cols = X.shape
+    ld = (cols + 15) // 16 * 16
+    out = torch.empty((nslices, rows, ld), dtype=torch.int8, device=X.device)
+    scale = torch.empty(rows, dtype=torch.float64, device=X.device)
+    check(lib.vt_ozaki_slice(ptr(X), _ld(X), rows, cols, ptr(out), ld, rows * ld, nslices, ptr(scale), ptr(fold),
+                             stream()))
+    return out, scale
+
+
+def ozaki_gemm(A, B, alpha=1.0, nslices=OZAKI_SLICES, out=None):
+    """out = alpha * A @ B.T for float64 A (M, K), B (N, K) on the INT8 tensor
+    cores (tcgen05.mma.kind::i8) with FP64-grade accuracy."""
+    lib = _cabi.require_cuda()
+    (M, K), (N, Kb) = A.shape, B.shape
+    if K != Kb:
+        raise ValueError('ozaki_gemm: inner dimensions differ ({} vs {})'.format(K, Kb))
+    As, sa = ozaki_slice(A, nslices)
+    Bs, sb = ozaki_slice(B, nslices)
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float64, device=A.device)
+    check(lib.vt_ozaki_gemm(M, N, K, ptr(As), As.stride(1), As.stride(0), ptr(Bs), Bs.stride(1), Bs.stride(0), nslices,
+                            float(alpha), ptr(sa), ptr(sb), ptr(out), _ld(out), stream()))
+    return out
+
+
 # ------------------------------------------------------- Hessian assembly ----
-PRECISIONS = {'f64': 0, 'tf32': 1, 'tf32x3': 3}
+PRECISIONS = {'f64': 0, 'tf32': 1, 'tf32x3': 3, 'f64_ozaki': 0}
 
 
 def _split(precision):
@@ -297,6 +330,11 @@ def ij_apply(Hinv, X, resid, out=None, precision='f64'):
     if out is None:
         out = torch.empty((D, N), dtype=torch.float64, device=X.device)
     split = _split(precision)
+    if precision == 'f64_ozaki':
+        ws, wsb = _ws('ij_ozaki', lib.vt_ij_apply_ozaki_workspace_bytes(N, D, OZAKI_SLICES), X.device)
+        check(lib.vt_ij_apply_ozaki(ptr(Hinv), _ld(Hinv), ptr(X), _ld(X), N, D, ptr(_f64(resid, 'resid')), ptr(out),
+                                    _ld(out), OZAKI_SLICES, ptr(ws), wsb, stream()))
+        return out
     if split:
         ws, wsb = _ws('ij_tf32', lib.vt_ij_apply_tf32_workspace_bytes(N, D, split), X.device)
         check(lib.vt_ij_apply_tf32(ptr(Hinv), _ld(Hinv), ptr(X), _ld(X), N, D, ptr(_f64(resid, 'resid')), ptr(out),

@@ -380,9 +380,9 @@ def main():
 
 
 ENGINE_NOTES = {
-    'f64_ozaki': ('H^-1 G^T apply on tcgen05.mma.kind::i8: 7 error-free 7-bit slices per operand, 28 exact INT8 '
-                  'products, INT32 accumulators in TMEM, INT64/FP64 recombination; Hessian, statistics, Cholesky in FP64 '
-                  '(DMMA); held to the same rtol 1e-8 bar as the default path'),
+    'f64_ozaki': ('both contractions on tcgen05.mma.kind::i8: 7 error-free 7-bit slices per operand, 28 exact INT8 '
+                  'products, INT32 accumulators in TMEM, INT64/FP64 recombination; statistics, Cholesky and inverse in '
+                  'FP64; held to the same rtol 1e-8 bar as the default path'),
     'tf32x3': 'both contractions on tcgen05.mma.kind::tf32 with a three-term hi/lo split; the rest in FP64',
     'tf32': 'both contractions on tcgen05.mma.kind::tf32 (TMEM accumulators, TMA operands); the rest in FP64',
 }
@@ -411,9 +411,8 @@ def engine_row(prec, vt, ops, torch, dist, world, group, dev, X, y, theta, w, st
                                                                    <= ENGINE_TOL[prec]),
            'ij_apply_ms': t_ap, 'ij_apply_fp64_equiv_tflops': 2.0 * D * D * n_loc / (t_ap * 1e-3) / 1e12,
            'engine': ENGINE_NOTES[prec]}
-    if prec != 'f64_ozaki':
-        t_sy, _h = timed(lambda: ops.syrk_weighted(X, st['s'], precision=prec), reps)
-        row.update({'syrk_ms': t_sy, 'syrk_tflops_algorithmic': float(D) * (D + 1) * n_loc / (t_sy * 1e-3) / 1e12})
+    t_sy, _h = timed(lambda: ops.syrk_weighted(X, st['s'], precision=prec), reps)
+    row.update({'syrk_ms': t_sy, 'syrk_fp64_equiv_tflops_algorithmic': float(D) * (D + 1) * n_loc / (t_sy * 1e-3) / 1e12})
     return row
 
 

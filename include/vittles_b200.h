@@ -15,9 +15,13 @@
  *     respect to the host unless stated otherwise;
  *   - the return value is 0 on success or a VT_ERR_* code; the message of the
  *     last failure on the calling thread is returned by vt_last_error();
- *   - the library holds no global state and never allocates device memory:
- *     workspaces are sized by the *_workspace_bytes queries and owned by the
- *     caller.
+ *   - the library never allocates device memory: workspaces are sized by the
+ *     *_workspace_bytes queries and owned by the caller, and it keeps no state
+ *     between calls.  (One experimental exception, off by default: with
+ *     VT_OZAKI_OVERLAP=1 in the environment the chunked INT8 drivers
+ *     vt_ij_apply_ozaki / vt_syrk_ozaki slice chunk c+1 on a helper stream -
+ *     created once per host thread and device, fenced against `stream` by
+ *     events on both sides - while the tensor cores multiply chunk c.)
  */
 #ifndef VITTLES_B200_H
 #define VITTLES_B200_H
@@ -161,6 +165,13 @@ int vt_ozaki_slice(const double* X, int64_t ldx, int64_t rows, int cols, int8_t*
 int vt_ozaki_gemm(int M, int N, int K, const int8_t* A, int64_t lda, int64_t a_slice_stride, const int8_t* B,
                   int64_t ldb, int64_t b_slice_stride, int nslices, double alpha, const double* rowscale,
                   const double* colscale, double* C, int64_t ldc, void* stream);
+/* vt_syrk_ozaki is vt_syrk_weighted (s >= 0) on the same engine: the contraction runs over the
+ * observations, so the digits of sqrt(s_n) x_ni are written transposed with one power-of-two
+ * scale per feature and per chunk of observations, and the chunks' lower-triangular Gram tiles
+ * (split-K parts of <= 16384 observations: the INT32 bound) are accumulated in FP64.            */
+size_t vt_syrk_ozaki_workspace_bytes(int64_t N, int D, int nslices);
+int vt_syrk_ozaki(const double* X, int64_t ldx, int64_t N, int D, const double* s, double l2, double* H, int64_t ldh,
+                  int nslices, void* workspace, size_t workspace_bytes, void* stream);
 size_t vt_ij_apply_ozaki_workspace_bytes(int64_t N, int D, int nslices);
 int vt_ij_apply_ozaki(const double* Hinv, int64_t ldh, const double* X, int64_t ldx, int64_t N, int D,
                       const double* resid, double* S, int64_t lds, int nslices, void* workspace,

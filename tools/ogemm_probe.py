@@ -12,7 +12,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-STAGES = ['slice', 'one', 'k1024', 'big', 'ragged', 's8', 'apply', 'time_apply', 'time_parts']
+STAGES = ['slice', 'one', 'k1024', 'big', 'ragged', 's8', 'apply', 'time_apply', 'time_parts', 'syrk', 'time_syrk']
 
 
 def run(stage):
@@ -134,6 +134,28 @@ def run(stage):
                               'slice_gb_per_s': nchunk * D * (8 + S) / ms_slice / 1e6, 'ms_gemm': ms_gemm,
                               'fp64_equiv_tflops': 2.0 * D * D * nchunk / ms_gemm / 1e9,
                               'int8_tops': 2.0 * D * D * nchunk * pairs / ms_gemm / 1e9}), flush=True)
+    elif stage in ('syrk', 'time_syrk'):
+        D = 1024
+        for N in ((777, 50000) if stage == 'syrk' else (1000000,)):
+            X = ops.synth_design(7, 0, N, D, dev)
+            s = torch.rand(N, device=dev, dtype=torch.float64, generator=g) * 0.25
+            ref = ops.syrk_weighted(X, s)
+            out = ops.syrk_weighted(X, s, precision='f64_ozaki')
+            torch.cuda.synchronize()
+            err = (out - ref).abs()
+            res = {'stage': stage, 'N': N, 'rel_max': float(err.max() / ref.abs().max()), 'symmetric': bool(torch.equal(out, out.T)),
+                   'rtol1e-8_atol1e-12max_ok': bool((err <= 1e-8 * ref.abs() + 1e-12 * ref.abs().max()).all()),
+                   'nan': bool(torch.isnan(out).any())}
+            if res['rel_max'] > 1e-6 or res['nan']:
+                res['row_bands'] = [round(float(err[i:i + 128].max()), 6) for i in range(0, D, 128)]
+                res['col_bands'] = [round(float(err[:, j:j + 64].max()), 6) for j in range(0, D, 64)]
+                res['out_00'] = [float(v) for v in out[0, :4]]
+                res['ref_00'] = [float(v) for v in ref[0, :4]]
+            if stage == 'time_syrk':
+                ms = timed(lambda: ops.syrk_weighted(X, s, out=out, precision='f64_ozaki'))
+                ms64 = timed(lambda: ops.syrk_weighted(X, s, out=ref), reps=1)
+                res.update({'ms': ms, 'fp64_equiv_tflops_algorithmic': float(D) * (D + 1) * N / ms / 1e9, 'ms_f64_dmma': ms64})
+            print(json.dumps(res), flush=True)
     else:
         raise SystemExit('unknown stage ' + stage)
 

@@ -256,6 +256,19 @@ int vt_ij_apply_ozaki(const double* Hinv, int64_t ldh, const double* X, int64_t 
   return ij_apply_ozaki(Hinv, ldh, X, ldx, N, D, resid, Sout, lds, nslices, workspace, workspace_bytes, S(stream));
 }
 
+size_t vt_syrk_ozaki_workspace_bytes(int64_t N, int D, int nslices) { return syrk_ozaki_workspace_bytes(N, D, nslices); }
+
+int vt_syrk_ozaki(const double* X, int64_t ldx, int64_t N, int D, const double* s, double l2, double* H, int64_t ldh,
+                  int nslices, void* workspace, size_t workspace_bytes, void* stream) {
+  int st = syrk_ozaki(X, ldx, N, D, s, H, ldh, nslices, workspace, workspace_bytes, S(stream));
+  if (st != VT_OK) return st;
+  if (l2 != 0.0) {
+    add_diag_kernel<<<(D + 255) / 256, 256, 0, S(stream)>>>(H, ldh, D, l2);
+    VT_LAUNCH_CHECK();
+  }
+  return VT_OK;
+}
+
 size_t vt_gemv_workspace_bytes(int M, int64_t N) { return gemv_workspace_bytes(M, N); }
 
 int vt_gemv(const double* A, int64_t lda, int M, int64_t N, const double* x, double alpha, const double* y0,

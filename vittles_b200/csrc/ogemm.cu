@@ -1,6 +1,7 @@
 // FP64-grade GEMM on the INT8 tensor cores by error-free slicing - see ogemm.cuh.
 #include "ogemm.cuh"
 #include "tc05.cuh"
+#include <cstdlib>
 
 namespace vt {
 
@@ -25,14 +26,52 @@ struct OCfg {
 };
 
 struct OKernelArgs {
-  int M, N, kblocks, tiles_m;
-  long ntiles;
+  int M, N, kblocks, tiles_m, tiles_n;
+  long ntiles;             // output tiles (all, or those touching the lower triangle)
+  int parts;               // split-K: unit u = part * ntiles + tile; part p writes C + p * part_stride
+  long units;
+  int lower;
+  int accumulate;          // C += result instead of C = result
+  long part_stride;
   double* C; long ldc;
   double alpha;
   const double* rowscale;
   const double* colscale;
   int c_vec;
 };
+
+// lower: row block tm keeps the column blocks 0 .. (tm*OBM + OBM-1) / OBN
+__host__ __device__ inline int o_lower_cols(int tm, int tiles_n) {
+  const int c = (tm * OBM + OBM - 1) / OBN + 1;
+  return c < tiles_n ? c : tiles_n;
+}
+struct OUnit {
+  int m0, n0, kb0, nkb, part;
+};
+__device__ __forceinline__ OUnit o_decode(const OKernelArgs& a, long u) {
+  OUnit r;
+  const long tile = u % a.ntiles;
+  r.part = (int)(u / a.ntiles);
+  int tm, tn;
+  if (!a.lower) {
+    tm = (int)(tile % a.tiles_m);       // row blocks fastest: CTAs that run together share the B slices in L2
+    tn = (int)(tile / a.tiles_m);
+  } else {
+    long t = tile;
+    for (tm = 0; tm < a.tiles_m - 1; ++tm) {
+      const int c = o_lower_cols(tm, a.tiles_n);
+      if (t < c) break;
+      t -= c;
+    }
+    tn = (int)t;
+  }
+  r.m0 = tm * OBM;
+  r.n0 = tn * OBN;
+  const int q = a.kblocks / a.parts, rem = a.kblocks % a.parts;
+  r.kb0 = r.part * q + (r.part < rem ? r.part : rem);
+  r.nkb = q + (r.part < rem ? 1 : 0);
+  return r;
+}
 
 // One CTA per SM walks output tiles (row blocks fastest, so that the CTAs running
 // together share the B slices in L2).  Per k-block the S slices of the B tile are
@@ -80,9 +119,10 @@ ogemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     if (elect_one()) {
       int bs = 0, as = 0;
       uint32_t bph = 0, aph = 0;
-      for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-        const int m0 = (int)(tile % a.tiles_m) * OBM, n0 = (int)(tile / a.tiles_m) * OBN;
-        for (int kb = 0; kb < a.kblocks; ++kb) {
+      for (long u = blockIdx.x; u < a.units; u += gridDim.x) {
+        const OUnit U = o_decode(a, u);
+        const int m0 = U.m0, n0 = U.n0;
+        for (int kb = U.kb0; kb < U.kb0 + U.nkb; ++kb) {
           mbar_wait_(bempty(bs), bph ^ 1u);
           mbar_arrive_expect_tx_(bfull(bs), (uint32_t)B_BUF_BYTES);
           tma_load_3d(sB0 + bs * B_BUF_BYTES, &mapB, bfull(bs), kb * OBK, n0, 0);        // box {128 B, 64 rows, S slices}
@@ -109,10 +149,12 @@ ogemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       const uint32_t desc_hi = (uint32_t)(d0 >> 32), desc_lo0 = (uint32_t)d0;
       int bs = 0, as = 0;
       uint32_t bph = 0, aph = 0, tph = 0;
-      for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+      for (long u = blockIdx.x; u < a.units; u += gridDim.x) {
+        const OUnit U = o_decode(a, u);
+        if (U.nkb == 0) continue;              // every role skips an empty unit
         mbar_wait_(tempty, tph ^ 1u);          // the epilogue has drained the accumulators of the previous tile
         tc_fence_after();
-        for (int kb = 0; kb < a.kblocks; ++kb) {
+        for (int kb = 0; kb < U.nkb; ++kb) {
           mbar_wait_(bfull(bs), bph);
           const uint32_t b_lo0 = desc_lo0 + ((sB0 + bs * B_BUF_BYTES) >> 4);
           const uint32_t first = kb == 0 ? 0u : 1u;
@@ -146,9 +188,12 @@ ogemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     uint32_t tph = 0;
     const double w_hi = 1.0 / 268435456.0;                        // 2^-28: accumulators 0..2 combined as P0 2^14 + P1 2^7 + P2
     const double w_lo = exp2(-7.0 * (double)(S + 1));             // accumulators 3..S-1 combined with P_{S-1} at weight 1
-    for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-      const int m0 = (int)(tile % a.tiles_m) * OBM, n0 = (int)(tile / a.tiles_m) * OBN;
+    for (long u = blockIdx.x; u < a.units; u += gridDim.x) {
+      const OUnit U = o_decode(a, u);
+      if (U.nkb == 0) continue;
+      const int m0 = U.m0, n0 = U.n0;
       const int grow = m0 + row_local;
+      double* Cpart = a.C + (long)U.part * a.part_stride;
       mbar_wait_(tfull, tph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
@@ -179,14 +224,18 @@ ogemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             const double cs = (a.colscale && gcol + j < a.N) ? a.colscale[gcol + j] : 1.0;
             out[j] = rs * cs * fma((double)lo[j], w_lo, (double)hi[j] * w_hi);
           }
-          double* cp = a.C + (long)grow * a.ldc + gcol;
+          double* cp = Cpart + (long)grow * a.ldc + gcol;
           if (a.c_vec && gcol + 16 <= a.N) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) st_global_v4(cp + j, out[j], out[j + 1], out[j + 2], out[j + 3]);
+            for (int j = 0; j < 16; j += 4) {
+              double o0 = 0.0, o1 = 0.0, o2 = 0.0, o3 = 0.0;
+              if (a.accumulate) ld_global_v4(cp + j, o0, o1, o2, o3);
+              st_global_v4(cp + j, o0 + out[j], o1 + out[j + 1], o2 + out[j + 2], o3 + out[j + 3]);
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              if (gcol + j < a.N) cp[j] = out[j];
+              if (gcol + j < a.N) cp[j] = (a.accumulate ? cp[j] : 0.0) + out[j];
           }
         }
       }
@@ -202,9 +251,18 @@ ogemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
-// One warp per row: row maximum -> power-of-two scale -> S truncated base-128 digits.
-// Every operation is exact in FP64 (scaling by powers of two, truncation, subtraction
-// of the truncated part), so sum_s d_s 2^{-7s} reproduces x / sigma to 7 S bits.
+// Digit s of the fixed-point value q = trunc(x 2^(7S) / sigma) (|q| < 2^(7S) <= 2^56): the 7-bit field of |q|
+// at bit `sh`, with the sign of q - i.e. truncation toward zero of x / sigma at every digit.  The scaling
+// by a power of two and the truncation are exact, and the fields are integer shifts and masks, so the
+// slicing costs two FP64-pipe operations per element instead of four per digit.
+__device__ __forceinline__ int digit_of(long long q, int sh) {
+  const unsigned long long a = (unsigned long long)(q < 0 ? -q : q);
+  const int f = (int)((a >> sh) & 127ull);
+  return q < 0 ? -f : f;
+}
+
+// One warp per row: row maximum -> power-of-two scale -> S truncated base-128 digits,
+// so that sum_s d_s 2^{-7s} reproduces x / sigma to 7 S bits.
 __global__ void __launch_bounds__(256) ozaki_slice_kernel(const double* __restrict__ X, long ldx, long rows, int cols,
                                                           int8_t* __restrict__ out, long ldo, long slice_stride,
                                                           int nslices, double* __restrict__ scale_out,
@@ -220,26 +278,129 @@ __global__ void __launch_bounds__(256) ozaki_slice_kernel(const double* __restri
     for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
     int e = 0;
     if (m > 0.0) (void)frexp(m, &e);                   // m = f 2^e, f in [0.5, 1)  ->  |x| 2^-e < 1
-    const double inv = ldexp(1.0, -e);
+    const double up = ldexp(1.0, 7 * nslices - e);     // x * up is an integer-valued |q| < 2^(7 S) after truncation
     if (lane == 0) scale_out[r] = ldexp(1.0, e) * (fold ? fold[r] : 1.0);
     // four consecutive elements per lane: one 4-byte store per slice, 128 contiguous bytes per warp
     for (int c0 = lane * 4; c0 < ldo; c0 += 128) {
-      double y[4];
+      long long q[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) y[j] = (c0 + j < cols) ? xr[c0 + j] * inv : 0.0;
+      for (int j = 0; j < 4; ++j) q[j] = (c0 + j < cols) ? __double2ll_rz(xr[c0 + j] * up) : 0;
       for (int s = 0; s < nslices; ++s) {
+        const int sh = 7 * (nslices - 1 - s);
         uint32_t packed = 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          y[j] *= 128.0;
-          const int d = __double2int_rz(y[j]);
-          y[j] -= (double)d;
-          packed |= ((uint32_t)d & 0xFFu) << (8 * j);
-        }
+        for (int j = 0; j < 4; ++j) packed |= ((uint32_t)digit_of(q[j], sh) & 0xFFu) << (8 * j);
         *reinterpret_cast<uint32_t*>(out + (long)s * slice_stride + r * ldo + c0) = packed;
       }
     }
   }
+}
+
+// ---- Hessian assembly: the contraction runs over the observations, so the digits are written
+// TRANSPOSED (out[s][feature][observation], observations contiguous = K-major for the same GEMM
+// kernel) and the power-of-two scale belongs to the feature (row of X^T), per chunk of observations.
+
+// colmax[i] = max_n sqrt(s_n) |x_ni| over the chunk, as the bit pattern of a non-negative double
+// (which orders like an unsigned integer) so that atomicMax can combine the CTAs.
+__global__ void __launch_bounds__(256) ozaki_colmax_kernel(const double* __restrict__ X, long ldx, long rows, int cols,
+                                                           const double* __restrict__ s, double* __restrict__ sq_out,
+                                                           unsigned long long* __restrict__ colmax) {
+  constexpr int ROWS_PER_STEP = 32;
+  __shared__ double sq[ROWS_PER_STEP];
+  const long nsteps = (rows + ROWS_PER_STEP - 1) / ROWS_PER_STEP;
+  constexpr int CPT = 8;                                   // columns per thread: up to 2048 features in one sweep
+  for (int cbase = 0; cbase < cols; cbase += CPT * 256) {
+    double m[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) m[j] = 0.0;
+    for (long st = blockIdx.x; st < nsteps; st += gridDim.x) {
+      const long r_begin = st * ROWS_PER_STEP;
+      const int nr = (int)(rows - r_begin < ROWS_PER_STEP ? rows - r_begin : ROWS_PER_STEP);
+      __syncthreads();
+      if (threadIdx.x < nr) {
+        // sqrt of the weight once per observation (also kept for the slicing kernel)
+        const double v = s ? sqrt(fmax(s[r_begin + threadIdx.x], 0.0)) : 1.0;
+        sq[threadIdx.x] = v;
+        if (cbase == 0) sq_out[r_begin + threadIdx.x] = v;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const int c = cbase + threadIdx.x + j * 256;
+        if (c < cols) {
+          double mm = m[j];
+#pragma unroll 8
+          for (int r = 0; r < nr; ++r) mm = fmax(mm, fabs(X[(r_begin + r) * ldx + c]) * sq[r]);
+          m[j] = mm;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+      const int c = cbase + threadIdx.x + j * 256;
+      if (c < cols) atomicMax(colmax + c, (unsigned long long)__double_as_longlong(m[j]));
+    }
+  }
+}
+
+// Tile of 128 observations x 32 features per CTA: coalesced FP64 reads along the features, digits
+// staged in shared memory ([slice][feature][observation], pitch 132 bytes: conflict free for the
+// feature-per-lane stores), 128-byte coalesced stores along the observations.
+constexpr int ST_OBS = 128, ST_FEAT = 32, ST_PITCH = ST_OBS + 4;
+__global__ void __launch_bounds__(256) ozaki_slice_t_kernel(const double* __restrict__ X, long ldx, long rows, int cols,
+                                                            const double* __restrict__ sq,
+                                                            const unsigned long long* __restrict__ colmax,
+                                                            int8_t* __restrict__ out, long ldo, long slice_stride,
+                                                            int nslices, double* __restrict__ scale_out) {
+  __shared__ __align__(16) int8_t sm[OZAKI_MAX_SLICES * ST_FEAT * ST_PITCH];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long tiles_x = (rows + ST_OBS - 1) / ST_OBS;
+  const int tiles_y = (cols + ST_FEAT - 1) / ST_FEAT;
+  for (long tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
+    const long n0 = (tile / tiles_y) * ST_OBS;          // feature blocks fastest: a CTA wave reads whole rows of X
+    const int i0 = (int)(tile % tiles_y) * ST_FEAT;
+    const int i = i0 + lane;
+    int e = 0;
+    if (i < cols) {
+      const double m = __longlong_as_double((long long)colmax[i]);
+      if (m > 0.0) (void)frexp(m, &e);
+      if (n0 == 0 && warp == 0) scale_out[i] = ldexp(1.0, e);
+    }
+    const double up = ldexp(1.0, 7 * nslices - e);
+#pragma unroll 4
+    for (int rr = warp; rr < ST_OBS; rr += 8) {
+      const long n = n0 + rr;
+      long long q = 0;
+      if (n < rows && i < cols) {
+        q = __double2ll_rz((X[n * ldx + i] * sq[n]) * up);  // |x sq| < 2^e: the column maximum used the same products
+      }
+      for (int sl = 0; sl < nslices; ++sl)
+        sm[(sl * ST_FEAT + lane) * ST_PITCH + rr] = (int8_t)digit_of(q, 7 * (nslices - 1 - sl));
+    }
+    __syncthreads();
+    // (slice, feature) rows of 128 bytes: one warp per row, 4 bytes per lane
+    for (int row = warp; row < nslices * ST_FEAT; row += 8) {
+      const int sl = row / ST_FEAT, f = row % ST_FEAT;
+      if (i0 + f < cols && n0 + 4 * lane < ldo) {
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(sm + row * ST_PITCH + 4 * lane);
+        *reinterpret_cast<uint32_t*>(out + (long)sl * slice_stride + (long)(i0 + f) * ldo + n0 + 4 * lane) = v;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// H = sum of the split-K partial buffers over the lower triangle, mirrored (exactly symmetric).
+__global__ void __launch_bounds__(256) ozaki_syrk_finish_kernel(const double* __restrict__ P, int parts, long part_stride,
+                                                                int D, double* __restrict__ H, long ldh) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)D * D) return;
+  const int r = (int)(idx / D), c = (int)(idx % D);
+  if (r < c) return;
+  double v = 0.0;
+  for (int p = 0; p < parts; ++p) v += P[(long)p * part_stride + (long)r * D + c];
+  H[(long)r * ldh + c] = v;
+  if (r != c) H[(long)c * ldh + r] = v;
 }
 
 // 3-D uint8 tensor map over the slices: dims {K, rows, S}, box {128, box_rows, box_slices}, 128-byte swizzle.
@@ -269,14 +430,54 @@ template <int S>
 int launch_s(const CUtensorMap& mA, const CUtensorMap& mB, const OKernelArgs& a, cudaStream_t stream) {
   auto kern = ogemm_kernel<S>;
   VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, OCfg<S>::SMEM_BYTES));
+  VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   const long slots = num_sms();
-  const int grid = (int)(a.ntiles < slots ? a.ntiles : slots);
+  const int grid = (int)(a.units < slots ? a.units : slots);
   kern<<<grid, O_THREADS, OCfg<S>::SMEM_BYTES, stream>>>(mA, mB, a);
   VT_LAUNCH_CHECK();
   return VT_OK;
 }
 
 inline size_t align_up(size_t x, size_t al) { return (x + al - 1) / al * al; }
+
+// The chunked drivers slice chunk c+1 (HBM bound) while the tensor cores multiply chunk c: the slicing
+// kernels run on a helper stream, fenced against the caller's stream with events, and share the SMs
+// with the one-CTA-per-SM GEMM (the GEMM CTA leaves ~35 KB of shared memory and 3/4 of the register
+// file free).  The helper stream and its events are created lazily, once per host thread and device -
+// the only state the library keeps between calls.
+// VT_OZAKI_OVERLAP=1 runs the slicing kernels on the helper stream (small persistent grids that can share
+// an SM with the resident GEMM CTA); the default runs everything on the caller's stream with full grids.
+bool ozaki_overlap() {
+  static const bool on = [] {
+    const char* e = getenv("VT_OZAKI_OVERLAP");
+    return e && e[0] == '1';
+  }();
+  return on;
+}
+
+struct SideLane {
+  int dev = -1;
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, ready[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr};
+};
+int side_lane(SideLane** out) {
+  static thread_local SideLane lane;
+  int dev = 0;
+  VT_CUDA(cudaGetDevice(&dev));
+  if (lane.dev != dev) {
+    SideLane fresh;
+    VT_CUDA(cudaStreamCreateWithFlags(&fresh.side, cudaStreamNonBlocking));
+    VT_CUDA(cudaEventCreateWithFlags(&fresh.fork, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) {
+      VT_CUDA(cudaEventCreateWithFlags(&fresh.ready[i], cudaEventDisableTiming));
+      VT_CUDA(cudaEventCreateWithFlags(&fresh.consumed[i], cudaEventDisableTiming));
+    }
+    fresh.dev = dev;
+    lane = fresh;          // (a lane created for another device is kept alive by the driver until exit)
+  }
+  *out = &lane;
+  return VT_OK;
+}
 
 long ozaki_chunk_rows(long N, int D, int nslices) {
   const long ld = (D + 15) / 16 * 16;
@@ -308,7 +509,7 @@ int ozaki_slice(const double* X, long ldx, long rows, int cols, int8_t* out, lon
   VT_REQUIRE(reinterpret_cast<uintptr_t>(out) % 16 == 0, "ozaki_slice: output must be 16-byte aligned");
   if (rows == 0) return VT_OK;
   long blocks = (rows + 7) / 8;
-  const long cap = (long)num_sms() * 8;
+  const long cap = (long)num_sms() * (ozaki_overlap() ? 4 : 8);      // overlapped: leave room for the resident GEMM CTA
   if (blocks > cap) blocks = cap;
   ozaki_slice_kernel<<<(unsigned)blocks, 256, 0, stream>>>(X, ldx, rows, cols, out, ldo, slice_stride, nslices, scale_out,
                                                           fold);
@@ -316,18 +517,26 @@ int ozaki_slice(const double* X, long ldx, long rows, int cols, int8_t* out, lon
   return VT_OK;
 }
 
-int ogemm_launch(int M, int N, int K, const int8_t* A, long lda, long a_slice_stride, const int8_t* B, long ldb,
-                 long b_slice_stride, int nslices, double alpha, const double* rowscale, const double* colscale, double* C,
-                 long ldc, cudaStream_t stream) {
+namespace {
+struct OLaunchOpts {
+  int lower = 0, parts = 1, accumulate = 0;
+  long part_stride = 0;
+};
+
+int ogemm_launch_opts(int M, int N, int K, const int8_t* A, long lda, long a_slice_stride, const int8_t* B, long ldb,
+                      long b_slice_stride, int nslices, double alpha, const double* rowscale, const double* colscale,
+                      double* C, long ldc, const OLaunchOpts& o, cudaStream_t stream) {
   VT_REQUIRE(M >= 0 && N >= 0 && K >= 1, "ogemm: bad dimensions");
   if (M == 0 || N == 0) return VT_OK;
   VT_REQUIRE(A && B && C, "ogemm: null operand");
   VT_REQUIRE(nslices >= 6 && nslices <= OZAKI_MAX_SLICES, "ogemm: 6, 7 or 8 slices are instantiated");
-  VT_REQUIRE(K <= OZAKI_MAX_K, "ogemm: K = %d exceeds %d (INT32 accumulation bound)", K, OZAKI_MAX_K);
+  VT_REQUIRE(o.parts >= 1 && (K + o.parts - 1) / o.parts <= OZAKI_MAX_K + OBK,
+             "ogemm: K = %d in %d part(s) exceeds %d per part (INT32 accumulation bound)", K, o.parts, OZAKI_MAX_K);
   VT_REQUIRE(lda % 16 == 0 && ldb % 16 == 0 && a_slice_stride % 16 == 0 && b_slice_stride % 16 == 0,
              "ogemm: pitches must be multiples of 16 bytes");
   VT_REQUIRE(reinterpret_cast<uintptr_t>(A) % 16 == 0 && reinterpret_cast<uintptr_t>(B) % 16 == 0,
              "ogemm: operands must be 16-byte aligned");
+  if (o.lower) VT_REQUIRE(M == N, "ogemm: lower-only output must be square");
   CUtensorMap mA, mB;
   int st = make_slice_map(&mA, A, M, K, lda, a_slice_stride, nslices, OBM, 1);
   if (st != VT_OK) return st;
@@ -337,23 +546,43 @@ int ogemm_launch(int M, int N, int K, const int8_t* A, long lda, long a_slice_st
   a.M = M; a.N = N;
   a.kblocks = (K + OBK - 1) / OBK;
   a.tiles_m = (M + OBM - 1) / OBM;
-  a.ntiles = (long)a.tiles_m * ((N + OBN - 1) / OBN);
+  a.tiles_n = (N + OBN - 1) / OBN;
+  a.lower = o.lower;
+  if (o.lower) {
+    a.ntiles = 0;
+    for (int tm = 0; tm < a.tiles_m; ++tm) a.ntiles += o_lower_cols(tm, a.tiles_n);
+  } else {
+    a.ntiles = (long)a.tiles_m * a.tiles_n;
+  }
+  a.parts = o.parts;
+  a.units = a.ntiles * a.parts;
+  a.accumulate = o.accumulate;
+  a.part_stride = o.part_stride;
   a.C = C; a.ldc = ldc;
   a.alpha = alpha;
   a.rowscale = rowscale; a.colscale = colscale;
-  a.c_vec = (ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(C) % 32 == 0);
+  a.c_vec = (ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(C) % 32 == 0) && (o.part_stride % 4 == 0);
   switch (nslices) {
     case 6: return launch_s<6>(mA, mB, a, stream);
     case 7: return launch_s<7>(mA, mB, a, stream);
     default: return launch_s<8>(mA, mB, a, stream);
   }
 }
+}  // namespace
+
+int ogemm_launch(int M, int N, int K, const int8_t* A, long lda, long a_slice_stride, const int8_t* B, long ldb,
+                 long b_slice_stride, int nslices, double alpha, const double* rowscale, const double* colscale, double* C,
+                 long ldc, cudaStream_t stream) {
+  VT_REQUIRE(K <= OZAKI_MAX_K, "ogemm: K = %d exceeds %d (INT32 accumulation bound)", K, OZAKI_MAX_K);
+  return ogemm_launch_opts(M, N, K, A, lda, a_slice_stride, B, ldb, b_slice_stride, nslices, alpha, rowscale, colscale, C,
+                           ldc, OLaunchOpts{}, stream);
+}
 
 size_t ij_apply_ozaki_workspace_bytes(long N, int D, int nslices) {
   const long ld = (D + 15) / 16 * 16;
   const long ch = ozaki_chunk_rows(N, D, nslices);
   return align_up((size_t)nslices * D * ld, 256) + align_up((size_t)D * 8, 256) +
-         align_up((size_t)nslices * ch * ld, 256) + align_up((size_t)ch * 8, 256);
+         2 * (align_up((size_t)nslices * ch * ld, 256) + align_up((size_t)ch * 8, 256));
 }
 
 int ij_apply_ozaki(const double* Hinv, long ldh, const double* X, long ldx, long N, int D, const double* resid,
@@ -370,19 +599,152 @@ int ij_apply_ozaki(const double* Hinv, long ldh, const double* X, long ldx, long
   w += align_up((size_t)nslices * D * ld, 256);
   double* sigma = reinterpret_cast<double*>(w);
   w += align_up((size_t)D * 8, 256);
-  int8_t* Bs = reinterpret_cast<int8_t*>(w);
-  w += align_up((size_t)nslices * ch * ld, 256);
-  double* tau = reinterpret_cast<double*>(w);
-  int st = ozaki_slice(Hinv, ldh, D, D, As, ld, (long)D * ld, nslices, sigma, nullptr, stream);
-  if (st != VT_OK) return st;
-  for (long r0 = 0; r0 < N; r0 += ch) {
-    const long rows = (N - r0 < ch) ? N - r0 : ch;
-    st = ozaki_slice(X + r0 * ldx, ldx, rows, D, Bs, ld, ch * ld, nslices, tau, resid + r0, stream);   // tau_n * resid_n
+  int8_t* Bs[2];
+  double* tau[2];
+  for (int b = 0; b < 2; ++b) {
+    Bs[b] = reinterpret_cast<int8_t*>(w);
+    w += align_up((size_t)nslices * ch * ld, 256);
+    tau[b] = reinterpret_cast<double*>(w);
+    w += align_up((size_t)ch * 8, 256);
+  }
+  const bool overlap = ozaki_overlap();
+  SideLane* L = nullptr;
+  int st = VT_OK;
+  cudaStream_t slicer = stream;
+  if (overlap) {
+    st = side_lane(&L);
     if (st != VT_OK) return st;
-    st = ogemm_launch(D, (int)rows, D, As, ld, (long)D * ld, Bs, ld, ch * ld, nslices, -1.0, sigma, tau, S + r0, lds,
+    VT_CUDA(cudaEventRecord(L->fork, stream));                  // the inputs are ready once `stream` gets here
+    VT_CUDA(cudaStreamWaitEvent(L->side, L->fork, 0));
+    slicer = L->side;
+  }
+  st = ozaki_slice(Hinv, ldh, D, D, As, ld, (long)D * ld, nslices, sigma, nullptr, stream);
+  if (st != VT_OK) return st;
+  long c = 0;
+  for (long r0 = 0; r0 < N; r0 += ch, ++c) {
+    const int b = (int)(c & 1);
+    const long rows = (N - r0 < ch) ? N - r0 : ch;
+    if (overlap && c >= 2) VT_CUDA(cudaStreamWaitEvent(L->side, L->consumed[b], 0));   // GEMM c-2 has read buffer b
+    st = ozaki_slice(X + r0 * ldx, ldx, rows, D, Bs[b], ld, ch * ld, nslices, tau[b], resid + r0, slicer);   // tau_n resid_n
+    if (st != VT_OK) return st;
+    if (overlap) {
+      VT_CUDA(cudaEventRecord(L->ready[b], L->side));
+      VT_CUDA(cudaStreamWaitEvent(stream, L->ready[b], 0));
+    }
+    st = ogemm_launch(D, (int)rows, D, As, ld, (long)D * ld, Bs[b], ld, ch * ld, nslices, -1.0, sigma, tau[b], S + r0, lds,
                       stream);
     if (st != VT_OK) return st;
+    if (overlap) VT_CUDA(cudaEventRecord(L->consumed[b], stream));
   }
+  return VT_OK;
+}
+
+// ---- H = X^T diag(s) X -----------------------------------------------------
+namespace {
+struct SyrkPlan {
+  int parts;
+  long chunk, ld;
+  size_t slices_bytes, cmax_bytes, scale_bytes, sq_bytes, part_bytes;
+};
+SyrkPlan syrk_plan(long N, int D, int nslices) {
+  SyrkPlan p;
+  const int tiles_m = (D + OBM - 1) / OBM, tiles_n = (D + OBN - 1) / OBN;
+  long ntiles = 0;
+  for (int tm = 0; tm < tiles_m; ++tm) ntiles += o_lower_cols(tm, tiles_n);
+  int parts = (int)(num_sms() / ntiles);
+  if (parts < 1) parts = 1;
+  if (parts > 8) parts = 8;
+  p.parts = parts;
+  long chunk = (long)parts * OZAKI_MAX_K;                       // every part accumulates at most 16384 observations in INT32
+  const size_t budget = (size_t)320 << 20;                      // all slices of one chunk
+  const long by_mem = (long)(budget / ((size_t)nslices * D)) / (parts * OBK) * (parts * OBK);
+  if (by_mem >= (long)parts * OBK && by_mem < chunk) chunk = by_mem;
+  if (chunk > N) chunk = N;
+  p.chunk = chunk;
+  p.ld = (chunk + 15) / 16 * 16;
+  p.slices_bytes = align_up((size_t)nslices * D * p.ld, 256);
+  p.cmax_bytes = align_up((size_t)D * 8, 256);
+  p.scale_bytes = align_up((size_t)D * 8, 256);
+  p.sq_bytes = align_up((size_t)N * 8, 256);
+  p.part_bytes = align_up((size_t)parts * D * D * 8, 256);
+  return p;
+}
+}  // namespace
+
+size_t syrk_ozaki_workspace_bytes(long N, int D, int nslices) {
+  const SyrkPlan p = syrk_plan(N, D, nslices);
+  return 2 * p.slices_bytes + p.cmax_bytes + p.scale_bytes + p.sq_bytes + p.part_bytes;
+}
+
+int syrk_ozaki(const double* X, long ldx, long N, int D, const double* s, double* H, long ldh, int nslices,
+               void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  VT_REQUIRE(X && H && workspace, "syrk_ozaki: null pointer");
+  VT_REQUIRE(D >= 1 && N >= 1 && ldx >= D && ldh >= D, "syrk_ozaki: bad shape");
+  VT_REQUIRE(nslices >= 6 && nslices <= OZAKI_MAX_SLICES, "syrk_ozaki: 6, 7 or 8 slices");
+  VT_REQUIRE(workspace_bytes >= syrk_ozaki_workspace_bytes(N, D, nslices), "syrk_ozaki: workspace too small");
+  const SyrkPlan p = syrk_plan(N, D, nslices);
+  char* w = static_cast<char*>(workspace);
+  int8_t* Xs[2];
+  for (int b = 0; b < 2; ++b) {
+    Xs[b] = reinterpret_cast<int8_t*>(w);
+    w += p.slices_bytes;
+  }
+  unsigned long long* cmax = reinterpret_cast<unsigned long long*>(w);
+  w += p.cmax_bytes;
+  double* sigma = reinterpret_cast<double*>(w);
+  w += p.scale_bytes;
+  double* sq = reinterpret_cast<double*>(w);
+  w += p.sq_bytes;
+  double* P = reinterpret_cast<double*>(w);
+  const long slice_stride = (long)D * p.ld;
+  // one sweep over all of X: sqrt of the weights and the per-feature maxima of sqrt(s_n) |x_ni| (the power-of-two
+  // scale of each row of X^T is common to all chunks: the error bound is relative to sigma_i sigma_j anyway)
+  VT_CUDA(cudaMemsetAsync(cmax, 0, (size_t)D * 8, stream));
+  {
+    long nsteps = (N + 31) / 32;
+    const long cap = (long)num_sms() * 8;
+    ozaki_colmax_kernel<<<(unsigned)(nsteps < cap ? nsteps : cap), 256, 0, stream>>>(X, ldx, N, D, s, sq, cmax);
+    VT_LAUNCH_CHECK();
+  }
+  VT_CUDA(cudaMemsetAsync(P, 0, (size_t)p.parts * D * D * 8, stream));      // every chunk (and part) accumulates
+  const bool overlap = ozaki_overlap();
+  SideLane* L = nullptr;
+  int st = VT_OK;
+  cudaStream_t slicer = stream;
+  if (overlap) {
+    st = side_lane(&L);
+    if (st != VT_OK) return st;
+    VT_CUDA(cudaEventRecord(L->fork, stream));
+    VT_CUDA(cudaStreamWaitEvent(L->side, L->fork, 0));
+    slicer = L->side;
+  }
+  long c = 0;
+  for (long r0 = 0; r0 < N; r0 += p.chunk, ++c) {
+    const int b = (int)(c & 1);
+    const long rows = (N - r0 < p.chunk) ? N - r0 : p.chunk;
+    if (overlap && c >= 2) VT_CUDA(cudaStreamWaitEvent(L->side, L->consumed[b], 0));
+    const long tiles = ((rows + ST_OBS - 1) / ST_OBS) * ((D + ST_FEAT - 1) / ST_FEAT);
+    const long cap = (long)num_sms() * (overlap ? 1 : 6);
+    ozaki_slice_t_kernel<<<(unsigned)(tiles < cap ? tiles : cap), 256, 0, slicer>>>(X + r0 * ldx, ldx, rows, D, sq + r0, cmax,
+                                                                                    Xs[b], p.ld, slice_stride, nslices, sigma);
+    VT_LAUNCH_CHECK();
+    if (overlap) {
+      VT_CUDA(cudaEventRecord(L->ready[b], L->side));
+      VT_CUDA(cudaStreamWaitEvent(stream, L->ready[b], 0));
+    }
+    OLaunchOpts o;
+    o.lower = 1;
+    o.parts = p.parts;
+    o.accumulate = 1;
+    o.part_stride = (long)D * D;
+    st = ogemm_launch_opts(D, D, (int)rows, Xs[b], p.ld, slice_stride, Xs[b], p.ld, slice_stride, nslices, 1.0, sigma, sigma,
+                           P, D, o, stream);
+    if (st != VT_OK) return st;
+    if (overlap) VT_CUDA(cudaEventRecord(L->consumed[b], stream));
+  }
+  const long total = (long)D * D;
+  ozaki_syrk_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(P, p.parts, (long)D * D, D, H, ldh);
+  VT_LAUNCH_CHECK();
   return VT_OK;
 }
 

@@ -40,4 +40,12 @@ size_t ij_apply_ozaki_workspace_bytes(long N, int D, int nslices);
 int ij_apply_ozaki(const double* Hinv, long ldh, const double* X, long ldx, long N, int D, const double* resid,
                    double* S, long lds, int nslices, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
+// H (D x D) = X^T diag(s) X (s >= 0) with FP64-grade accuracy on the INT8 tensor cores: per chunk of
+// observations the digits of sqrt(s_n) x_ni are written transposed with one power-of-two scale per
+// feature, the lower tiles of the chunk's Gram matrix run as split-K parts of at most 16384
+// observations (INT32 bound) and are accumulated in FP64.
+size_t syrk_ozaki_workspace_bytes(long N, int D, int nslices);
+int syrk_ozaki(const double* X, long ldx, long N, int D, const double* s, double* H, long ldh, int nslices,
+               void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
 }  // namespace vt

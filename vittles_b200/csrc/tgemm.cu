@@ -132,7 +132,7 @@ tgemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ 
 
   if (warp == 0) {
     // ================================================== TMA producer ====
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (long u = blockIdx.x; u < a.units; u += gridDim.x) {
@@ -168,7 +168,7 @@ tgemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ==================================================== MMA issuer ====
-    if (lane == 0) {
+    if (elect_one()) {
       // instruction descriptor: D = F32, A = B = TF32, majors, N >> 3, M >> 4
       constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(AMODE == T_KS) << 15) |
                                  ((uint32_t)(BMODE == T_KS) << 16) | ((uint32_t)(BN >> 3) << 17) |
@@ -181,6 +181,9 @@ tgemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ 
       constexpr uint32_t A_LT = AMODE == T_KC ? 2u : 1u, B_LT = BMODE == T_KC ? 2u : 1u;
       constexpr uint32_t A_KSTEP = AMODE == T_KC ? (UMMA_K * 4) : (UMMA_K * 128);
       constexpr uint32_t B_KSTEP = BMODE == T_KC ? (UMMA_K * 4) : (UMMA_K * 128);
+      const uint64_t da0 = umma_desc(0u, A_LBO, A_SBO, A_LT), db0 = umma_desc(0u, B_LBO, B_SBO, B_LT);
+      const uint32_t a_hi = (uint32_t)(da0 >> 32), a_lo0 = (uint32_t)da0;
+      const uint32_t b_hi = (uint32_t)(db0 >> 32), b_lo0 = (uint32_t)db0;
       int stage = 0;
       uint32_t phase = 0;
       uint32_t it = 0;                       // accumulator-stage use counter
@@ -198,19 +201,18 @@ tgemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ 
             tc_fence_after();
             const uint32_t sA = smem_base + stage * STAGE_BYTES;
             const uint32_t sB = sA + NOPS * A_BYTES;
+            // descriptor lo halves of this stage (the hi halves are loop invariant): one add per operand per MMA
+            const uint32_t a_lo = a_lo0 + (sA >> 4), b_lo = b_lo0 + (sB >> 4);
 #pragma unroll
             for (int kk = 0; kk < TBK / UMMA_K; ++kk) {
-              const uint64_t ah = umma_desc(sA + kk * A_KSTEP, A_LBO, A_SBO, A_LT);
-              const uint64_t bh = umma_desc(sB + kk * B_KSTEP, B_LBO, B_SBO, B_LT);
+              const uint32_t ak = a_lo + kk * (A_KSTEP >> 4), bk = b_lo + kk * (B_KSTEP >> 4);
               const uint32_t acc0 = (kb > kb_begin || kk > 0) ? 1u : 0u;
               if (NOPS == 1) {
-                umma_tf32(tmem_d, ah, bh, idesc, acc0);
+                umma_tf32_lohi(tmem_d, ak, a_hi, bk, b_hi, idesc, acc0);
               } else {
-                const uint64_t al = umma_desc(sA + A_BYTES + kk * A_KSTEP, A_LBO, A_SBO, A_LT);
-                const uint64_t bl = umma_desc(sB + B_BYTES + kk * B_KSTEP, B_LBO, B_SBO, B_LT);
-                umma_tf32(tmem_d, al, bh, idesc, acc0);     // small terms first
-                umma_tf32(tmem_d, ah, bl, idesc, 1u);
-                umma_tf32(tmem_d, ah, bh, idesc, 1u);
+                umma_tf32_lohi(tmem_d, ak + (A_BYTES >> 4), a_hi, bk, b_hi, idesc, acc0);     // small terms first
+                umma_tf32_lohi(tmem_d, ak, a_hi, bk + (B_BYTES >> 4), b_hi, idesc, 1u);
+                umma_tf32_lohi(tmem_d, ak, a_hi, bk, b_hi, idesc, 1u);
               }
             }
             umma_commit(empty_bar(stage));                   // smem slot free once these MMAs have read it

@@ -184,8 +184,9 @@ def _split(precision):
 
 
 def syrk_weighted(X, s=None, l2=0.0, out=None, precision='f64'):
-    """H = X^T diag(s) X + l2 I  (FP64 DMMA, deterministic split-K; or the
-    optional TF32 / TF32x3 tcgen05 path, which needs s >= 0)."""
+    """H = X^T diag(s) X + l2 I  (FP64 DMMA, deterministic split-K; or, for
+    s >= 0, the INT8 error-free-slicing engine 'f64_ozaki' (FP64-grade) or the
+    optional reduced-precision TF32 / TF32x3 tcgen05 path)."""
     lib = _cabi.require_cuda()
     _mat(X, 'X')
     N, D = X.shape
@@ -198,6 +199,14 @@ def syrk_weighted(X, s=None, l2=0.0, out=None, precision='f64'):
             raise ValueError('s must have one entry per row of X')
     if out is None:
         out = torch.empty((D, D), dtype=torch.float64, device=X.device)
+    if (split or precision == 'f64_ozaki') and s is not None and bool((s < 0).any()):
+        raise ValueError("syrk_weighted: precision {!r} needs non-negative weights (it factors out sqrt(s)); "
+                         "use precision='f64'".format(precision))
+    if precision == 'f64_ozaki':
+        ws, wsb = _ws('syrk_ozaki', lib.vt_syrk_ozaki_workspace_bytes(N, D, OZAKI_SLICES), X.device)
+        check(lib.vt_syrk_ozaki(ptr(X), _ld(X), N, D, ptr(s), float(l2), ptr(out), _ld(out), OZAKI_SLICES, ptr(ws), wsb,
+                                stream()))
+        return out
     if split:
         ws, wsb = _ws('syrk_tf32', lib.vt_syrk_tf32_workspace_bytes(N, D, split), X.device)
         check(lib.vt_syrk_tf32(ptr(X), _ld(X), N, D, ptr(s), float(l2), ptr(out), _ld(out), split, ptr(ws), wsb,

@@ -49,6 +49,8 @@ def parse():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-tf32', action='store_true', help='skip the rows of the other engines (f64_ozaki, tf32x3, tf32)')
+    ap.add_argument('--engines', action='store_true', help='also measure the other engines when --gpus > 1 '
+                    '(by default they are measured on 1 GPU only)')
     return ap.parse_args()
 
 
@@ -289,7 +291,7 @@ def main():
     # instead of it: 'f64_ozaki' (FP64-grade apply on the INT8 tensor cores, same parity bar) and the
     # optional reduced-precision 'tf32x3' / 'tf32' rows (tcgen05 TF32 engine, stated tolerances).
     engine_rows = None
-    if not args.no_tf32:
+    if not args.no_tf32 and (world == 1 or args.engines):
         import gc
         engine_rows = {}
         for prec in ('f64_ozaki', 'tf32x3', 'tf32'):
@@ -380,7 +382,7 @@ def main():
 
 
 ENGINE_NOTES = {
-    'f64_ozaki': ('both contractions on tcgen05.mma.kind::i8: 7 error-free 7-bit slices per operand, 28 exact INT8 '
+    'f64_ozaki': ('both contractions on tcgen05.mma.kind::i8: 8 error-free 7-bit slices per operand (56 bits), 36 exact INT8 '
                   'products, INT32 accumulators in TMEM, INT64/FP64 recombination; statistics, Cholesky and inverse in '
                   'FP64; held to the same rtol 1e-8 bar as the default path'),
     'tf32x3': 'both contractions on tcgen05.mma.kind::tf32 with a three-term hi/lo split; the rest in FP64',
@@ -402,13 +404,16 @@ def engine_row(prec, vt, ops, torch, dist, world, group, dev, X, y, theta, w, st
     S32 = sens32.get_dopt_dhyper()
     del sens32
     diff = torch.abs(S32[:, idx] - S_cols64)
-    err_norm = float(torch.max(diff) / torch.max(torch.abs(S_cols64)))
-    err_elem = float(torch.max(diff / (torch.abs(S_cols64) + 1e-12 * torch.max(torch.abs(S_cols64)))))
+    smax = torch.max(torch.abs(S_cols64))
+    err_norm = float(torch.max(diff) / smax)
+    # the parity bar of tests/conftest.py::assert_close: |diff| <= rtol |ref| + 1e-12 max|ref|, as the worst ratio
+    bar = float(torch.max(diff / (1e-8 * torch.abs(S_cols64) + 1e-12 * smax)))
     t_ap, _ = timed(lambda: ops.ij_apply(hinv, X, st['resid'], out=S32, precision=prec), reps)
     row = {'value': N / (t_step * 1e-3), 'unit': UNIT, 'ms_per_step': t_step,
-           'sampled_sens_err_vs_f64_dmma': {'normwise': err_norm, 'elementwise_with_1e-12_floor': err_elem},
-           'tolerance': ENGINE_TOL[prec], 'within_tolerance': bool((err_elem if prec == 'f64_ozaki' else err_norm)
-                                                                   <= ENGINE_TOL[prec]),
+           'sampled_sens_err_vs_f64_dmma': {'normwise': err_norm, 'worst_ratio_to_rtol1e-8_bar': bar},
+           'tolerance': ('rtol 1e-8 elementwise + 1e-12 max|ref| floor (the FP64 parity bar)' if prec == 'f64_ozaki'
+                         else '{:g} normwise'.format(ENGINE_TOL[prec])),
+           'within_tolerance': bool(bar <= 1.0) if prec == 'f64_ozaki' else bool(err_norm <= ENGINE_TOL[prec]),
            'ij_apply_ms': t_ap, 'ij_apply_fp64_equiv_tflops': 2.0 * D * D * n_loc / (t_ap * 1e-3) / 1e12,
            'engine': ENGINE_NOTES[prec]}
     t_sy, _h = timed(lambda: ops.syrk_weighted(X, st['s'], precision=prec), reps)

@@ -46,7 +46,7 @@ def test_slicing_is_exact_to_7S_bits(vt, S):
 def test_ozaki_gemm_is_fp64_grade(vt, shape):
     M, N, K = shape
     A, B = _rnd(M, K, seed=3), _rnd(N, K, seed=4)
-    out = vt.ops.ozaki_gemm(A, B, alpha=-2.0)
+    out = vt.ops.ozaki_gemm(A, B, alpha=-2.0, nslices=7)
     assert_close(out, -2.0 * (A @ B.T), rtol=1e-8, atol_scale=1e-12, what='ozaki_gemm {}'.format(shape))
     out8 = vt.ops.ozaki_gemm(A, B, alpha=-2.0, nslices=8)
     assert float((out8 + 2.0 * (A @ B.T)).abs().max() / (A @ B.T).abs().max()) < 1e-12
@@ -56,10 +56,28 @@ def test_ozaki_gemm_badly_scaled_rows(vt):
     """Row scales spanning 12 orders of magnitude: the per-row power-of-two scaling keeps every row at 49 bits."""
     A = _rnd(256, 512, seed=5) * torch.exp(6 * _rnd(256, 1, seed=6))
     B = _rnd(192, 512, seed=7) * torch.exp(6 * _rnd(192, 1, seed=8))
-    out = vt.ops.ozaki_gemm(A, B)
+    out = vt.ops.ozaki_gemm(A, B, nslices=7)
     ref = A @ B.T
     rowcol = A.abs().max(dim=1).values[:, None] * B.abs().max(dim=1).values[None, :]
     assert float(((out - ref).abs() / rowcol).max()) < 1e-10
+
+
+def test_seven_slices_stay_inside_the_parity_bar(vt, monkeypatch):
+    """The engine's default is 8 digits (56 bits); 7 digits (49 bits, 28 instead of 36 products) still meet rtol 1e-8
+    on well-scaled data but sit close to the 1e-12 max|ref| floor, which is why they are not the default."""
+    monkeypatch.setattr(vt.ops, 'OZAKI_SLICES', 7)
+    N, D = 20000, 512
+    X = vt.ops.synth_design(21, 0, N, D, 'cuda')
+    Hm = _rnd(D, D, seed=13)
+    Hinv = torch.linalg.inv(Hm @ Hm.T / D + 0.05 * torch.eye(D, device='cuda', dtype=torch.float64)).contiguous()
+    resid = _rnd(N, seed=14)
+    S64 = vt.ops.ij_apply(Hinv, X, resid)
+    S7 = vt.ops.ij_apply(Hinv, X, resid, precision='f64_ozaki')
+    assert float((S7 - S64).abs().max() / S64.abs().max()) < 5e-12
+    s = torch.rand(N, device='cuda', dtype=torch.float64)
+    H64 = vt.ops.syrk_weighted(X, s)
+    H7 = vt.ops.syrk_weighted(X, s, precision='f64_ozaki')
+    assert float((H7 - H64).abs().max() / H64.abs().max()) < 5e-12
 
 
 def test_ij_apply_on_the_int8_engine(vt):

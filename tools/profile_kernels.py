@@ -39,5 +39,9 @@ S32 = H32 = None
 for prec in ('tf32', 'tf32x3'):
     S32 = ops.ij_apply(hinv, X[:NT], resid[:NT], precision=prec)
     H32 = ops.syrk_weighted(X[:NT], s[:NT].abs(), precision=prec)
+# FP64-grade INT8 engine (tcgen05.mma.kind::i8): two chunks of the apply and of the Hessian assembly
+NO = min(N, 2 * 32768)
+So = ops.ij_apply(hinv, X[:NO], resid[:NO], precision='f64_ozaki')
+Ho = ops.syrk_weighted(X[:NO], s[:NO].abs(), precision='f64_ozaki')
 torch.cuda.synchronize()
 print('profile run done', float(H[0, 0]), float(q[0]), float(dd[0]), float(p[0]))

@@ -30,6 +30,8 @@ COLS = [('gpu__time_duration.sum', 'duration'), ('dram__bytes_read.sum', 'dram_r
         ('smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio', 'stall_barrier'),
         ('smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio', 'stall_lg_throttle'),
         ('l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'smem_bank_conflicts')]
+COLS += [('sm__inst_executed_pipe_tc.sum', 'inst_pipe_tc'), ('sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_elapsed', 'tc_pipe_pct'),
+         ('lts__t_bytes.sum', 'l2_bytes'), ('l1tex__m_xbar2l1tex_read_bytes.sum', 'l2_to_sm_bytes')]
 COLS = [(c, n) for c, n in COLS if c in idx]
 SCALE = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}
 best = {}

@@ -13,7 +13,7 @@ from . import _cabi
 from ._cabi import check, ptr, stream
 
 _workspaces = {}
-OZAKI_SLICES = 7      # digits per operand of the 'f64_ozaki' engine (49 bits; 8 -> 56 bits)
+OZAKI_SLICES = 8      # digits per operand of the 'f64_ozaki' engine: 56 bits >= the 53-bit significand (7 -> 49 bits, ~25% faster)
 
 
 def _ws(key, nbytes, device):

@@ -22,4 +22,4 @@ The reference's own closed-form test fixtures (QuadraticModel, MVN KL, block
 quadratic, weighted least squares) are re-created in ``oracle/fixtures.py`` and
 asserted in ``tests/test_oracle.py``.
 """
-from . import solver_lib, sensitivity, sparse_hessian, lr_cov, bivariate, models, fixtures  # noqa: F401
+from . import solver_lib, sensitivity, sparse_hessian, lr_cov, bivariate, models, fixtures, slicing  # noqa: F401

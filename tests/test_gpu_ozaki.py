@@ -41,6 +41,22 @@ def test_slicing_is_exact_to_7S_bits(vt, S):
     assert torch.equal(sc2, sc * fold)
 
 
+@pytest.mark.parametrize('S', [7, 8])
+def test_digits_and_products_match_the_cpu_model_exactly(vt, S):
+    """Integer work: bit-exact against the oracle's model of the engine (oracle/slicing.py) - the digits, the scales
+    and, up to the last FP64 roundings of the recombination, the product."""
+    from oracle import slicing
+    A = _rnd(150, 333, seed=20) * torch.exp(2 * _rnd(150, 1, seed=21))
+    B = _rnd(70, 333, seed=22)
+    d, sc = vt.ops.ozaki_slice(A, S)
+    d_ref, sc_ref = slicing.slice_rows(A.cpu().numpy(), S)
+    assert np.array_equal(d[:, :, :333].cpu().numpy(), d_ref)
+    assert np.array_equal(sc.cpu().numpy(), sc_ref)
+    out = vt.ops.ozaki_gemm(A, B, nslices=S).cpu().numpy()
+    model = slicing.sliced_gemm(A.cpu().numpy(), B.cpu().numpy(), S)
+    np.testing.assert_allclose(out, model, rtol=1e-15, atol=1e-16 * np.abs(model).max())
+
+
 @pytest.mark.parametrize('shape', [(128, 64, 128), (1024, 1024, 1024), (200, 300, 100), (130, 515, 1000), (1, 1, 1),
                                    (257, 65, 36)])
 def test_ozaki_gemm_is_fp64_grade(vt, shape):

@@ -182,3 +182,29 @@ def test_synth_generator_statistics():
     assert np.array_equal(a, b)                      # any row range is reproducible
     u = models.synth_uniform(3, 0, 10000)
     assert 0.0 <= u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 0.02
+
+
+@pytest.mark.parametrize('nslices', [6, 7, 8])
+def test_int8_slicing_model_is_error_free_and_bounded(nslices):
+    """The arithmetic model of the INT8 engine (oracle/slicing.py): the digits reproduce every operand to
+    7 S bits of its row scale, every accumulator stays inside INT32 at K = 1024, and the recombined product is
+    within the analytic bound of the float64 product - without a GPU."""
+    from oracle import slicing
+    rng = np.random.RandomState(7)
+    a = rng.normal(size=(40, 1024)) * np.exp(3 * rng.normal(size=(40, 1)))
+    b = rng.normal(size=(24, 1024)) * np.exp(3 * rng.normal(size=(24, 1)))
+    a[3] = 0.0
+    d, sc = slicing.slice_rows(a, nslices)
+    assert d.dtype == np.int8 and np.max(np.abs(d.astype(np.int64))) <= 127
+    assert np.all(np.frexp(sc)[0] == 0.5) and np.all(sc > np.max(np.abs(a), axis=1))
+    resid = np.max(np.abs(a - slicing.reconstruct(d, sc)), axis=1)
+    assert np.all(resid <= sc * 2.0 ** (-7 * nslices) * (1 + 2.0 ** -40))
+    # digits carry the sign of the element (truncation toward zero)
+    assert np.all((d.astype(np.int64) * np.sign(a)[None]) >= 0)
+    out = slicing.sliced_gemm(a, b, nslices)
+    exact = a @ b.T
+    sa, sb = sc, slicing.slice_rows(b, nslices)[1]
+    bound = slicing.error_bound(a.shape[1], nslices) * sa[:, None] * sb[None, :] + 1e-15 * np.abs(exact)
+    assert np.all(np.abs(out - exact) <= bound)
+    if nslices >= 7:
+        np.testing.assert_allclose(out, exact, rtol=1e-8, atol=1e-12 * np.max(np.abs(exact)))

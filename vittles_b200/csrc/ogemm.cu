@@ -255,10 +255,30 @@ ogemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
 // at bit `sh`, with the sign of q - i.e. truncation toward zero of x / sigma at every digit.  The scaling
 // by a power of two and the truncation are exact, and the fields are integer shifts and masks, so the
 // slicing costs two FP64-pipe operations per element instead of four per digit.
-__device__ __forceinline__ int digit_of(long long q, int sh) {
+// Four values at once: |q| is split once into its low four digits (28 bits) and the rest, each digit is then a 32-bit shift + mask, the sign one multiply, and PRMT packs the four
+// int8 digits of slice `sl` (0 = most significant of `nslices`) into one word (byte j = value j).
+struct Fixed4 {
+  uint32_t lo[4], hi[4];
+  int sgn[4];
+};
+__device__ __forceinline__ void fixed4_set(Fixed4& f, int j, long long q) {
   const unsigned long long a = (unsigned long long)(q < 0 ? -q : q);
-  const int f = (int)((a >> sh) & 127ull);
-  return q < 0 ? -f : f;
+  f.lo[j] = (uint32_t)a & 0x0FFFFFFFu;
+  f.hi[j] = (uint32_t)(a >> 28);
+  f.sgn[j] = q < 0 ? -1 : 1;
+}
+__device__ __forceinline__ uint32_t fixed4_digits(const Fixed4& f, int sl, int nslices) {
+  const int pos = nslices - 1 - sl;              // digit position from the least significant one
+  int d[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t w = pos < 4 ? f.lo[j] : f.hi[j];
+    const int sh = 7 * (pos < 4 ? pos : pos - 4);
+    d[j] = (int)((w >> sh) & 127u) * f.sgn[j];
+  }
+  const uint32_t p01 = __byte_perm((uint32_t)d[0], (uint32_t)d[1], 0x0040);
+  const uint32_t p23 = __byte_perm((uint32_t)d[2], (uint32_t)d[3], 0x0040);
+  return __byte_perm(p01, p23, 0x5410);
 }
 
 // One warp per row: row maximum -> power-of-two scale -> S truncated base-128 digits,
@@ -282,16 +302,11 @@ __global__ void __launch_bounds__(256) ozaki_slice_kernel(const double* __restri
     if (lane == 0) scale_out[r] = ldexp(1.0, e) * (fold ? fold[r] : 1.0);
     // four consecutive elements per lane: one 4-byte store per slice, 128 contiguous bytes per warp
     for (int c0 = lane * 4; c0 < ldo; c0 += 128) {
-      long long q[4];
+      Fixed4 f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) q[j] = (c0 + j < cols) ? __double2ll_rz(xr[c0 + j] * up) : 0;
-      for (int s = 0; s < nslices; ++s) {
-        const int sh = 7 * (nslices - 1 - s);
-        uint32_t packed = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) packed |= ((uint32_t)digit_of(q[j], sh) & 0xFFu) << (8 * j);
-        *reinterpret_cast<uint32_t*>(out + (long)s * slice_stride + r * ldo + c0) = packed;
-      }
+      for (int j = 0; j < 4; ++j) fixed4_set(f, j, (c0 + j < cols) ? __double2ll_rz(xr[c0 + j] * up) : 0ll);
+      for (int s = 0; s < nslices; ++s)
+        *reinterpret_cast<uint32_t*>(out + (long)s * slice_stride + r * ldo + c0) = fixed4_digits(f, s, nslices);
     }
   }
 }
@@ -367,15 +382,19 @@ __global__ void __launch_bounds__(256) ozaki_slice_t_kernel(const double* __rest
       if (n0 == 0 && warp == 0) scale_out[i] = ldexp(1.0, e);
     }
     const double up = ldexp(1.0, 7 * nslices - e);
-#pragma unroll 4
-    for (int rr = warp; rr < ST_OBS; rr += 8) {
-      const long n = n0 + rr;
-      long long q = 0;
-      if (n < rows && i < cols) {
-        q = __double2ll_rz((X[n * ldx + i] * sq[n]) * up);  // |x sq| < 2^e: the column maximum used the same products
+    // four consecutive observations per step: their digits of one slice pack into one 32-bit shared-memory store
+#pragma unroll 2
+    for (int rr = 4 * warp; rr < ST_OBS; rr += 32) {
+      Fixed4 f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const long n = n0 + rr + j;
+        long long q = 0;
+        if (n < rows && i < cols) q = __double2ll_rz((X[n * ldx + i] * sq[n]) * up);   // |x sq| < 2^e (same products as colmax)
+        fixed4_set(f, j, q);
       }
       for (int sl = 0; sl < nslices; ++sl)
-        sm[(sl * ST_FEAT + lane) * ST_PITCH + rr] = (int8_t)digit_of(q, 7 * (nslices - 1 - sl));
+        *reinterpret_cast<uint32_t*>(sm + (sl * ST_FEAT + lane) * ST_PITCH + rr) = fixed4_digits(f, sl, nslices);
     }
     __syncthreads();
     // (slice, feature) rows of 128 bytes: one warp per row, 4 bytes per lane

@@ -416,6 +416,15 @@ def engine_row(prec, vt, ops, torch, dist, world, group, dev, X, y, theta, w, st
            'within_tolerance': bool(bar <= 1.0) if prec == 'f64_ozaki' else bool(err_norm <= ENGINE_TOL[prec]),
            'ij_apply_ms': t_ap, 'ij_apply_fp64_equiv_tflops': 2.0 * D * D * n_loc / (t_ap * 1e-3) / 1e12,
            'engine': ENGINE_NOTES[prec]}
+    if prec == 'f64_ozaki':
+        S_ = ops.OZAKI_SLICES
+        tops = 2.0 * D * D * n_loc * (S_ * (S_ + 1) // 2) / (t_ap * 1e-3) / 1e12
+        row['ij_apply_roofline'] = {'bound': 'tensor (INT8)', 'achieved': tops, 'peak': 4500.0, 'unit': 'TOP/s',
+                                    'frac': tops / 4500.0,
+                                    'peak_source': 'nominal dense INT8 peak of B200 (MEASURED_PEAKS.json has no INT8 entry)',
+                                    'algorithmic': '{} digit products of 2*D^2 INT8 ops per observation ({} slices); '
+                                                   'ncu: sm__pipe_tc_cycles_active 90 % (profiles/ncu_full_r01d_kernels.csv)'
+                                                   .format(S_ * (S_ + 1) // 2, S_)}
     t_sy, _h = timed(lambda: ops.syrk_weighted(X, st['s'], precision=prec), reps)
     row.update({'syrk_ms': t_sy, 'syrk_fp64_equiv_tflops_algorithmic': float(D) * (D + 1) * n_loc / (t_sy * 1e-3) / 1e12})
     return row

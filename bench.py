@@ -49,6 +49,8 @@ def parse():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-tf32', action='store_true', help='skip the rows of the other engines (f64_ozaki, tf32x3, tf32)')
+    ap.add_argument('--precision', default='f64', choices=['f64', 'f64_ozaki', 'tf32x3', 'tf32'],
+                    help="engine of the two contractions for the headline and e2e legs (default: FP64 DMMA)")
     ap.add_argument('--engines', action='store_true', help='also measure the other engines when --gpus > 1 '
                     '(by default they are measured on 1 GPU only)')
     return ap.parse_args()
@@ -213,7 +215,7 @@ def main():
     y = ops.synth_bernoulli(SEED, r0, z_star)
     del z_star, zeros
     w = torch.ones(n_loc, dtype=torch.float64, device=dev)
-    obj = vt.objectives.GLMObjective(X, y, family='logistic', group=group)
+    obj = vt.objectives.GLMObjective(X, y, family='logistic', group=group, precision=args.precision)
 
     # ---- optimum by Newton's method on the same kernels (setup, untimed) ----
     theta = torch.zeros(D, dtype=torch.float64, device=dev)
@@ -346,8 +348,10 @@ def main():
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong',
-            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'vs_baseline': None, 'dtype': {'f64': 'f64', 'f64_ozaki': 'i8 digit slices -> f64 (error-free slicing)',
+                                           'tf32x3': 'tf32x3', 'tf32': 'tf32'}[args.precision], 'data': 'synthetic',
             'config': {'workload': 'logistic IJ N=10M D=1024 f64 (BASELINE configs[1])', 'n_obs': N, 'dim': D,
+                       'precision': args.precision,
                        'sharding': 'observations over {} rank(s), one all-reduce of the DxD Hessian'.format(world),
                        'l2': 'inputs ({:.1f} GB per rank) exceed the 126 MB L2'.format(8.0 * n_loc * D / 1e9),
                        'grad_norm_at_opt': grad_norm, 'sampled_residual_rel': rel_resid},
@@ -459,7 +463,7 @@ def run_e2e(args, vt, torch, dist, dev, group, world, host):
     def step():
         # host (pinned) buffers straight into the public API: GLMObjective starts chunked
         # asynchronous copies and the statistics + Hessian sweep runs behind them
-        o = vt.objectives.GLMObjective(X_host, y_host, family='logistic', group=group)
+        o = vt.objectives.GLMObjective(X_host, y_host, family='logistic', group=group, precision=args.precision)
         sens = vt.HyperparameterSensitivityLinearApproximation(o, theta_host, w_host)
         pred = sens.predict_opt_par_from_hyper_par(w1_host)      # D doubles, returned on the host
         hess = sens.get_hessian_at_opt()                         # D x D, returned on the host

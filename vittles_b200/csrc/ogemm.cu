@@ -79,7 +79,9 @@ __device__ __forceinline__ OUnit o_decode(const OKernelArgs& a, long u) {
 // ring; slice s of A meets slices t = 0 .. S-1-s of B, and product (s, t) goes to
 // accumulator s + t.  Every INT8 tile loaded is used by (S+1)/2 products on
 // average, which keeps the L2 -> shared-memory traffic at ~47 B/clk/SM at the
-// tensor peak.
+// tensor peak.  Measured (ncu, S = 8): tensor pipe 90 % active at 65 clk per
+// 128x64x32 MMA - the N = 64 tile that the S accumulators force is bound by the
+// shared-memory operand reads (6 KB per MMA), not by L2 or by issue.
 template <int S>
 __global__ void __launch_bounds__(O_THREADS, 1)
 ogemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const OKernelArgs a) {
@@ -251,12 +253,13 @@ ogemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
-// Digit s of the fixed-point value q = trunc(x 2^(7S) / sigma) (|q| < 2^(7S) <= 2^56): the 7-bit field of |q|
-// at bit `sh`, with the sign of q - i.e. truncation toward zero of x / sigma at every digit.  The scaling
-// by a power of two and the truncation are exact, and the fields are integer shifts and masks, so the
-// slicing costs two FP64-pipe operations per element instead of four per digit.
-// Four values at once: |q| is split once into its low four digits (28 bits) and the rest, each digit is then a 32-bit shift + mask, the sign one multiply, and PRMT packs the four
-// int8 digits of slice `sl` (0 = most significant of `nslices`) into one word (byte j = value j).
+// Digit s of the fixed-point value q = trunc(x 2^(7S) / sigma) (|q| < 2^(7S) <= 2^56) is the 7-bit field of |q|
+// at bit 7 (S-1-s), with the sign of q - truncation toward zero of x / sigma at every digit.  The scaling by a
+// power of two and the truncation are exact and the fields are integer shifts and masks, so the slicing costs
+// two FP64-pipe operations per element.  Four values at once: |q| is split once into its low four digits
+// (28 bits) and the rest, each digit is then a 32-bit shift + mask, the sign one multiply, and PRMT packs the
+// four int8 digits of slice `sl` (0 = most significant of `nslices`) into one word (byte j = value j).
+// (oracle/slicing.py is the CPU model; tests/test_gpu_ozaki.py compares digit for digit.)
 struct Fixed4 {
   uint32_t lo[4], hi[4];
   int sgn[4];
@@ -313,9 +316,9 @@ __global__ void __launch_bounds__(256) ozaki_slice_kernel(const double* __restri
 
 // ---- Hessian assembly: the contraction runs over the observations, so the digits are written
 // TRANSPOSED (out[s][feature][observation], observations contiguous = K-major for the same GEMM
-// kernel) and the power-of-two scale belongs to the feature (row of X^T), per chunk of observations.
+// kernel) and the power-of-two scale belongs to the feature (row of X^T).
 
-// colmax[i] = max_n sqrt(s_n) |x_ni| over the chunk, as the bit pattern of a non-negative double
+// colmax[i] = max_n sqrt(s_n) |x_ni| over all rows given, as the bit pattern of a non-negative double
 // (which orders like an unsigned integer) so that atomicMax can combine the CTAs.
 __global__ void __launch_bounds__(256) ozaki_colmax_kernel(const double* __restrict__ X, long ldx, long rows, int cols,
                                                            const double* __restrict__ s, double* __restrict__ sq_out,
@@ -459,13 +462,12 @@ int launch_s(const CUtensorMap& mA, const CUtensorMap& mB, const OKernelArgs& a,
 
 inline size_t align_up(size_t x, size_t al) { return (x + al - 1) / al * al; }
 
-// The chunked drivers slice chunk c+1 (HBM bound) while the tensor cores multiply chunk c: the slicing
-// kernels run on a helper stream, fenced against the caller's stream with events, and share the SMs
-// with the one-CTA-per-SM GEMM (the GEMM CTA leaves ~35 KB of shared memory and 3/4 of the register
-// file free).  The helper stream and its events are created lazily, once per host thread and device -
-// the only state the library keeps between calls.
-// VT_OZAKI_OVERLAP=1 runs the slicing kernels on the helper stream (small persistent grids that can share
-// an SM with the resident GEMM CTA); the default runs everything on the caller's stream with full grids.
+// Experimental, off by default (VT_OZAKI_OVERLAP=1): slice chunk c+1 on a helper stream while the tensor
+// cores multiply chunk c - small persistent slicing grids that can share an SM with the resident GEMM CTA,
+// fenced against the caller's stream with events.  Measured on B200 it is not faster (Hessian 30 ms vs 21 ms
+// per 1M observations: the two kernels end up serialised and the small grids are slow on their own), so the
+// default runs everything on the caller's stream with full grids.  The helper stream and its events are
+// created lazily, once per host thread and device, only when the switch is on.
 bool ozaki_overlap() {
   static const bool on = [] {
     const char* e = getenv("VT_OZAKI_OVERLAP");

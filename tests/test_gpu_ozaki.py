@@ -146,6 +146,29 @@ def test_ij_sensitivities_through_the_api_match_the_oracle(vt):
     assert_close(sens.get_hessian_at_opt(), ref['hessian'], rtol=1e-9)
 
 
+def test_non_finite_inputs_propagate_like_fp64(vt):
+    """An Inf / NaN in an operand row poisons exactly the results FP64 arithmetic would poison (the digits of a
+    non-finite value are meaningless, so its row gets a NaN scale)."""
+    N, D = 3000, 96
+    X = vt.ops.synth_design(17, 0, N, D, 'cuda')
+    Hinv = torch.eye(D, device='cuda', dtype=torch.float64) + 0.05 * _rnd(D, D, seed=30)
+    resid = _rnd(N, seed=31)
+    X[5, 7] = float('nan')
+    X[11, 3] = float('inf')
+    S = vt.ops.ij_apply(Hinv, X, resid, precision='f64_ozaki')
+    bad = torch.isnan(S).any(dim=0)
+    assert bool(bad[5]) and bool(bad[11]) and int(bad.sum()) == 2
+    assert bool(torch.isnan(S[:, 5]).all()) and bool(torch.isnan(S[:, 11]).all())
+    ok = ~bad
+    assert_close(S[:, ok], vt.ops.ij_apply(Hinv, X, resid)[:, ok], rtol=1e-8, atol_scale=1e-12)
+    H = vt.ops.syrk_weighted(X, torch.ones(N, device='cuda', dtype=torch.float64), precision='f64_ozaki')
+    nan_rows = torch.isnan(H).all(dim=1)
+    assert sorted(torch.nonzero(nan_rows).flatten().tolist()) == [3, 7]
+    keep = [i for i in range(D) if i not in (3, 7)]
+    Xc = X[:, keep].contiguous()
+    assert_close(H[keep][:, keep], vt.ops.syrk_weighted(Xc), rtol=1e-8, atol_scale=1e-12)
+
+
 def test_bad_arguments(vt):
     A = _rnd(8, 20000)
     with pytest.raises(ValueError):

@@ -296,13 +296,20 @@ __global__ void __launch_bounds__(256) ozaki_slice_kernel(const double* __restri
   for (long r = warp0; r < rows; r += nwarps) {
     const double* xr = X + r * ldx;
     double m = 0.0;
-    for (int c = lane; c < cols; c += 32) m = fmax(m, fabs(xr[c]));
+    bool finite = true;                                // fmax() drops NaNs: track non-finite entries separately
+    for (int c = lane; c < cols; c += 32) {
+      const double v = fabs(xr[c]);
+      finite = finite && (v <= 1.7976931348623157e308);
+      m = fmax(m, v);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    finite = __all_sync(0xffffffffu, finite);
     int e = 0;
-    if (m > 0.0) (void)frexp(m, &e);                   // m = f 2^e, f in [0.5, 1)  ->  |x| 2^-e < 1
+    if (finite && m > 0.0) (void)frexp(m, &e);         // m = f 2^e, f in [0.5, 1)  ->  |x| 2^-e < 1
     const double up = ldexp(1.0, 7 * nslices - e);     // x * up is an integer-valued |q| < 2^(7 S) after truncation
-    if (lane == 0) scale_out[r] = ldexp(1.0, e) * (fold ? fold[r] : 1.0);
+    // a row with an Inf or NaN gets a NaN scale: every result that touches it is NaN, as in FP64 arithmetic
+    if (lane == 0) scale_out[r] = finite ? ldexp(1.0, e) * (fold ? fold[r] : 1.0) : __longlong_as_double(0x7ff8000000000000LL);
     // four consecutive elements per lane: one 4-byte store per slice, 128 contiguous bytes per warp
     for (int c0 = lane * 4; c0 < ldo; c0 += 128) {
       Fixed4 f;
@@ -337,7 +344,11 @@ __global__ void __launch_bounds__(256) ozaki_colmax_kernel(const double* __restr
       __syncthreads();
       if (threadIdx.x < nr) {
         // sqrt of the weight once per observation (also kept for the slicing kernel)
-        const double v = s ? sqrt(fmax(s[r_begin + threadIdx.x], 0.0)) : 1.0;
+        double v = 1.0;
+        if (s) {
+          const double sv = s[r_begin + threadIdx.x];
+          v = (sv == sv) ? sqrt(fmax(sv, 0.0)) : sv;         // a NaN weight stays NaN (fmax would drop it)
+        }
         sq[threadIdx.x] = v;
         if (cbase == 0) sq_out[r_begin + threadIdx.x] = v;
       }
@@ -348,7 +359,11 @@ __global__ void __launch_bounds__(256) ozaki_colmax_kernel(const double* __restr
         if (c < cols) {
           double mm = m[j];
 #pragma unroll 8
-          for (int r = 0; r < nr; ++r) mm = fmax(mm, fabs(X[(r_begin + r) * ldx + c]) * sq[r]);
+          for (int r = 0; r < nr; ++r) {
+            const double v = fabs(X[(r_begin + r) * ldx + c]) * sq[r];
+            // a non-finite product poisons the column: the quiet-NaN pattern is above every finite one in atomicMax
+            mm = (v <= 1.7976931348623157e308 && mm == mm) ? fmax(mm, v) : __longlong_as_double(0x7ff8000000000000LL);
+          }
           m[j] = mm;
         }
       }
@@ -381,8 +396,9 @@ __global__ void __launch_bounds__(256) ozaki_slice_t_kernel(const double* __rest
     int e = 0;
     if (i < cols) {
       const double m = __longlong_as_double((long long)colmax[i]);
-      if (m > 0.0) (void)frexp(m, &e);
-      if (n0 == 0 && warp == 0) scale_out[i] = ldexp(1.0, e);
+      const bool finite = m <= 1.7976931348623157e308;
+      if (finite && m > 0.0) (void)frexp(m, &e);
+      if (n0 == 0 && warp == 0) scale_out[i] = finite ? ldexp(1.0, e) : m;   // NaN scale: row and column i of H become NaN
     }
     const double up = ldexp(1.0, 7 * nslices - e);
     // four consecutive observations per step: their digits of one slice pack into one 32-bit shared-memory store

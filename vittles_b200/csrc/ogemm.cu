@@ -255,20 +255,24 @@ ogemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
 
 // Digit s of the fixed-point value q = trunc(x 2^(7S) / sigma) (|q| < 2^(7S) <= 2^56) is the 7-bit field of |q|
 // at bit 7 (S-1-s), with the sign of q - truncation toward zero of x / sigma at every digit.  The scaling by a
-// power of two and the truncation are exact and the fields are integer shifts and masks, so the slicing costs
-// two FP64-pipe operations per element.  Four values at once: |q| is split once into its low four digits
-// (28 bits) and the rest, each digit is then a 32-bit shift + mask, the sign one multiply, and PRMT packs the
-// four int8 digits of slice `sl` (0 = most significant of `nslices`) into one word (byte j = value j).
+// power of two and the truncations are exact and the fields are integer shifts and masks.  Four values at
+// once: |q| is held as its low four digits (28 bits) and the rest, each digit is then a 32-bit shift + mask,
+// the sign one multiply, and PRMT packs the four int8 digits of slice `sl` (0 = most significant of
+// `nslices`) into one word (byte j = value j).
 // (oracle/slicing.py is the CPU model; tests/test_gpu_ozaki.py compares digit for digit.)
 struct Fixed4 {
   uint32_t lo[4], hi[4];
   int sgn[4];
 };
-__device__ __forceinline__ void fixed4_set(Fixed4& f, int j, long long q) {
-  const unsigned long long a = (unsigned long long)(q < 0 ? -q : q);
-  f.lo[j] = (uint32_t)a & 0x0FFFFFFFu;
-  f.hi[j] = (uint32_t)(a >> 28);
-  f.sgn[j] = q < 0 ? -1 : 1;
+// t = x * 2^(7 (S-4)) / sigma (|t| < 2^28 for S <= 8): the integer part of |t| holds the digits above the low
+// four, its fraction times 2^28 the low four.  Only 32-bit conversions (a 64-bit one is emulated in software
+// and made the slicers instruction bound); every step is exact in FP64.
+__device__ __forceinline__ void fixed4_set(Fixed4& f, int j, double t) {
+  const double a = fabs(t);
+  const uint32_t hi = __double2uint_rz(a);
+  f.hi[j] = hi;
+  f.lo[j] = __double2uint_rz((a - (double)hi) * 268435456.0) & 0x0FFFFFFFu;
+  f.sgn[j] = t < 0.0 ? -1 : 1;
 }
 __device__ __forceinline__ uint32_t fixed4_digits(const Fixed4& f, int sl, int nslices) {
   const int pos = nslices - 1 - sl;              // digit position from the least significant one
@@ -307,14 +311,14 @@ __global__ void __launch_bounds__(256) ozaki_slice_kernel(const double* __restri
     finite = __all_sync(0xffffffffu, finite);
     int e = 0;
     if (finite && m > 0.0) (void)frexp(m, &e);         // m = f 2^e, f in [0.5, 1)  ->  |x| 2^-e < 1
-    const double up = ldexp(1.0, 7 * nslices - e);     // x * up is an integer-valued |q| < 2^(7 S) after truncation
+    const double up = ldexp(1.0, 7 * (nslices - 4) - e);   // |x * up| < 2^(7 (S-4)): digits above / below the binary point
     // a row with an Inf or NaN gets a NaN scale: every result that touches it is NaN, as in FP64 arithmetic
     if (lane == 0) scale_out[r] = finite ? ldexp(1.0, e) * (fold ? fold[r] : 1.0) : __longlong_as_double(0x7ff8000000000000LL);
     // four consecutive elements per lane: one 4-byte store per slice, 128 contiguous bytes per warp
     for (int c0 = lane * 4; c0 < ldo; c0 += 128) {
       Fixed4 f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) fixed4_set(f, j, (c0 + j < cols) ? __double2ll_rz(xr[c0 + j] * up) : 0ll);
+      for (int j = 0; j < 4; ++j) fixed4_set(f, j, (c0 + j < cols) ? xr[c0 + j] * up : 0.0);
       for (int s = 0; s < nslices; ++s)
         *reinterpret_cast<uint32_t*>(out + (long)s * slice_stride + r * ldo + c0) = fixed4_digits(f, s, nslices);
     }
@@ -400,7 +404,7 @@ __global__ void __launch_bounds__(256) ozaki_slice_t_kernel(const double* __rest
       if (finite && m > 0.0) (void)frexp(m, &e);
       if (n0 == 0 && warp == 0) scale_out[i] = finite ? ldexp(1.0, e) : m;   // NaN scale: row and column i of H become NaN
     }
-    const double up = ldexp(1.0, 7 * nslices - e);
+    const double up = ldexp(1.0, 7 * (nslices - 4) - e);
     // four consecutive observations per step: their digits of one slice pack into one 32-bit shared-memory store
 #pragma unroll 2
     for (int rr = 4 * warp; rr < ST_OBS; rr += 32) {
@@ -408,9 +412,9 @@ __global__ void __launch_bounds__(256) ozaki_slice_t_kernel(const double* __rest
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const long n = n0 + rr + j;
-        long long q = 0;
-        if (n < rows && i < cols) q = __double2ll_rz((X[n * ldx + i] * sq[n]) * up);   // |x sq| < 2^e (same products as colmax)
-        fixed4_set(f, j, q);
+        double t = 0.0;
+        if (n < rows && i < cols) t = (X[n * ldx + i] * sq[n]) * up;   // |x sq| < 2^e (same products as colmax)
+        fixed4_set(f, j, t);
       }
       for (int sl = 0; sl < nslices; ++sl)
         *reinterpret_cast<uint32_t*>(sm + (sl * ST_FEAT + lane) * ST_PITCH + rr) = fixed4_digits(f, sl, nslices);

@@ -153,3 +153,32 @@ def test_block_arrow_detection_host_logic():
     assert detect_block_arrow((r @ r.T + scipy.sparse.eye(80)).tocoo()) is None
     ragged = scipy.sparse.block_diag([np.ones((3, 3)), np.ones((4, 4))])
     assert detect_block_arrow(ragged) is None
+
+
+def test_engine_selection_host_logic():
+    """precision= is validated on the host before anything touches a device; workspace queries of the
+    tensor-core engines need no GPU and grow the way the chunked drivers slice."""
+    import vittles_b200 as vt
+    from vittles_b200 import _cabi, ops
+    assert ops._split('f64') == 0 and ops._split('f64_ozaki') == 0 and ops._split('tf32') == 1 and ops._split('tf32x3') == 3
+    with pytest.raises(ValueError, match='precision'):
+        ops._split('bf16')
+    with pytest.raises(ValueError, match='precision'):
+        vt.objectives.GLMObjective(np.ones((4, 2)), np.ones(4), precision='fp16')
+    assert ops.OZAKI_SLICES in (6, 7, 8)
+    lib = _cabi.load()
+    # INT8 engine: slices of H^-1 + two chunk buffers of X slices (chunk: a whole number of 64-row tiles, < 64K rows)
+    small = lib.vt_ij_apply_ozaki_workspace_bytes(1000, 1024, 8)
+    big = lib.vt_ij_apply_ozaki_workspace_bytes(10_000_000, 1024, 8)
+    assert 8 * 1024 * 1024 < small < big < (1 << 30)
+    assert lib.vt_ij_apply_ozaki_workspace_bytes(10_000_000, 1024, 7) < big
+    # Hessian assembly: N doubles of sqrt(s) + two chunk buffers + split-K partial Hessians
+    w = lib.vt_syrk_ozaki_workspace_bytes(10_000_000, 1024, 8)
+    assert 8 * 10_000_000 < w < (1 << 30)
+    # TF32 engine: FP32 copies of one chunk (x2 for the hi/lo split)
+    t1 = lib.vt_ij_apply_tf32_workspace_bytes(10_000_000, 1024, 1)
+    t3 = lib.vt_ij_apply_tf32_workspace_bytes(10_000_000, 1024, 3)
+    assert 0 < t1 < (1 << 29) and t1 < t3 < (1 << 30)
+    assert lib.vt_syrk_tf32_workspace_bytes(10_000_000, 1024, 1) > 0
+    assert lib.vt_tf32_gemm_workspace_bytes(1024, 1024, 1 << 20, 1) > 0     # long K: split-K partial tiles
+    assert lib.vt_tf32_gemm_workspace_bytes(1024, 1 << 20, 1024, 1) == 0    # many tiles, short K: direct epilogue

@@ -506,6 +506,8 @@ size_t ws_bytes_for(int M, int N, long K, int split, int lower, int parts) {
   int P = parts > 0 ? parts : pick_parts(ntiles, kblocks);
   if (P > kblocks) P = kblocks;
   if (P < 1) P = 1;
+  // one part and one FP32 accumulation segment: the epilogue scales and stores directly, no partial tiles
+  if (!lower && P == 1 && kblocks <= SEG_KBLOCKS) return 0;
   return (size_t)ntiles * P * TBM * BN * 8;
 }
 

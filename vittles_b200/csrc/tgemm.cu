@@ -489,6 +489,7 @@ int tgemm_dispatch(const TLaunch& L, cudaStream_t stream) {
   VT_REQUIRE(p.M >= 0 && p.N >= 0 && p.K >= 0, "tgemm: negative dimension");
   if (p.M == 0 || p.N == 0) return VT_OK;
   VT_REQUIRE(p.A_hi && p.B_hi && (p.C || !L.finalize), "tgemm: null operand");
+  VT_REQUIRE(p.K > 0, "tgemm: K must be positive");
   VT_REQUIRE((p.A_lo == nullptr) == (p.B_lo == nullptr), "tgemm: give both or neither low-order operand");
   VT_REQUIRE(p.lda % 4 == 0 && p.ldb % 4 == 0, "tgemm: operand leading dimensions must be multiples of 4 floats");
   VT_REQUIRE(reinterpret_cast<uintptr_t>(p.A_hi) % 16 == 0 && reinterpret_cast<uintptr_t>(p.B_hi) % 16 == 0,

@@ -51,6 +51,7 @@ def parse():
     ap.add_argument('--no-tf32', action='store_true', help='skip the rows of the other engines (f64_ozaki, tf32x3, tf32)')
     ap.add_argument('--precision', default='f64', choices=['f64', 'f64_ozaki', 'tf32x3', 'tf32'],
                     help="engine of the two contractions for the headline and e2e legs (default: FP64 DMMA)")
+    ap.add_argument('--engine-rows-only', action='store_true', help=argparse.SUPPRESS)   # child mode, see main()
     ap.add_argument('--engines', action='store_true', help='also measure the other engines when --gpus > 1 '
                     '(by default they are measured on 1 GPU only)')
     return ap.parse_args()
@@ -290,10 +291,13 @@ def main():
     del S, G_cols, resid_check
 
     # ---- other engines for the two contractions, reported next to the FP64 DMMA headline, never
-    # instead of it: 'f64_ozaki' (FP64-grade apply on the INT8 tensor cores, same parity bar) and the
+    # instead of it: 'f64_ozaki' (FP64-grade contractions on the INT8 tensor cores, same parity bar) and the
     # optional reduced-precision 'tf32x3' / 'tf32' rows (tcgen05 TF32 engine, stated tolerances).
+    # On one GPU they are measured in a CHILD process after everything else (see the end of main): a device
+    # fault in an optional engine must never cost the headline line.  With several ranks (--engines) they run here.
     engine_rows = None
-    if not args.no_tf32 and (world == 1 or args.engines):
+    want_rows = not args.no_tf32 and (world == 1 or args.engines)
+    if args.engine_rows_only or (want_rows and world > 1):
         import gc
         engine_rows = {}
         for prec in ('f64_ozaki', 'tf32x3', 'tf32'):
@@ -304,6 +308,9 @@ def main():
                 engine_rows[prec] = {'error': repr(exc)[:300]}
             gc.collect()
             torch.cuda.empty_cache()
+        if args.engine_rows_only:
+            print(json.dumps({'other_engines': engine_rows}))
+            return
     del S_cols64
 
     peaks = {}
@@ -322,12 +329,14 @@ def main():
 
     # ---- end to end: HOST buffers in, host result out ---------------------------
     e2e = None
+    freed = False
     if not args.no_e2e:
         try:
             host = stage_to_host(torch, X, y, theta)
             # free every device-resident tensor of the resident phase: the e2e step brings its own
             obj.X = obj.y = obj = None
             del X, y, st, H, hinv, w
+            freed = True
             ops.free_workspaces()
             torch.cuda.empty_cache()
             e2e = run_e2e(args, vt, torch, dist, dev, group, world, host)
@@ -343,6 +352,26 @@ def main():
         cpu_baseline = {'value': n_s / sec, 'unit': UNIT, 'cores': blas_threads(), 'kind': 'port',
                         'sample': '{} of {} observations, D={}; numpy closed-form assembly + '
                                   'cho_factor/cho_solve (oracle port of the reference path)'.format(n_s, N, D)}
+
+    if want_rows and world == 1:
+        # the other engines, in a child process with the device to itself (this process keeps only its context)
+        import gc
+        if not freed:
+            obj.X = obj.y = obj = None
+            del X, y, st, H, hinv, w
+        host = None
+        ops.free_workspaces()
+        gc.collect()
+        torch.cuda.empty_cache()
+        cmd = [sys.executable, os.path.abspath(__file__), '--engine-rows-only', '--n-total', str(N), '--dim', str(D),
+               '--steps', str(min(args.steps, 3)), '--warmup', '1', '--no-e2e', '--no-cpu-baseline']
+        try:
+            child = subprocess.run(cmd, capture_output=True, text=True, timeout=1500)
+            lines = [ln for ln in child.stdout.splitlines() if ln.startswith('{')]
+            engine_rows = json.loads(lines[-1])['other_engines'] if lines else {
+                'error': 'child exited with code {}: {}'.format(child.returncode, child.stderr[-300:])}
+        except Exception as exc:              # report, never hide
+            engine_rows = {'error': repr(exc)[:300]}
 
     if rank == 0:
         line = {

@@ -184,27 +184,40 @@ def test_synth_generator_statistics():
     assert 0.0 <= u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 0.02
 
 
-@pytest.mark.parametrize('nslices', [6, 7, 8])
+@pytest.mark.parametrize('nslices', [5, 6, 7])
 def test_int8_slicing_model_is_error_free_and_bounded(nslices):
-    """The arithmetic model of the INT8 engine (oracle/slicing.py): the digits reproduce every operand to
-    7 S bits of its row scale, every accumulator stays inside INT32 at K = 1024, and the recombined product is
-    within the analytic bound of the float64 product - without a GPU."""
+    """The arithmetic model of the INT8 engine (oracle/slicing.py): the balanced base-256 digits reproduce every
+    operand to 8 S - 1 bits of its row scale, every accumulator stays inside INT32 at K = 1024 (the model asserts it),
+    and the recombined product is within the analytic bound of the float64 product - without a GPU."""
     from oracle import slicing
     rng = np.random.RandomState(7)
     a = rng.normal(size=(40, 1024)) * np.exp(3 * rng.normal(size=(40, 1)))
     b = rng.normal(size=(24, 1024)) * np.exp(3 * rng.normal(size=(24, 1)))
     a[3] = 0.0
     d, sc = slicing.slice_rows(a, nslices)
-    assert d.dtype == np.int8 and np.max(np.abs(d.astype(np.int64))) <= 127
+    assert d.dtype == np.int8 and np.abs(d[0].astype(np.int64)).max() <= 65      # |x| / scale < 1: top digit <= 64 + carry
     assert np.all(np.frexp(sc)[0] == 0.5) and np.all(sc > np.max(np.abs(a), axis=1))
     resid = np.max(np.abs(a - slicing.reconstruct(d, sc)), axis=1)
-    assert np.all(resid <= sc * 2.0 ** (-7 * nslices) * (1 + 2.0 ** -40))
-    # digits carry the sign of the element (truncation toward zero)
-    assert np.all((d.astype(np.int64) * np.sign(a)[None]) >= 0)
+    assert np.all(resid <= sc * 2.0 ** (-(8 * nslices - 1)) * (1 + 2.0 ** -40))   # round to nearest: half a unit
+    # the digits are an exact positional representation of q = rint(x 2^(8S-2) / scale)
+    q = sum(d[s].astype(np.int64) << (8 * (nslices - 1 - s)) for s in range(nslices))
+    assert np.array_equal(q, np.rint(np.ldexp(a, (8 * nslices - 2 - np.frexp(sc)[1] + 1)[:, None])).astype(np.int64))
     out = slicing.sliced_gemm(a, b, nslices)
     exact = a @ b.T
     sa, sb = sc, slicing.slice_rows(b, nslices)[1]
     bound = slicing.error_bound(a.shape[1], nslices) * sa[:, None] * sb[None, :] + 1e-15 * np.abs(exact)
     assert np.all(np.abs(out - exact) <= bound)
-    if nslices >= 7:
+    if nslices >= 6:
         np.testing.assert_allclose(out, exact, rtol=1e-8, atol=1e-12 * np.max(np.abs(exact)))
+
+
+def test_int8_slicing_model_extreme_digits():
+    """Every digit -128 (the largest magnitude a balanced digit takes) at the largest K a split-K part may have
+    (16384 + one k-block): the INT32 accumulators of the model (asserted inside digits_gemm) do not overflow."""
+    from oracle import slicing
+    S, K = 7, 16384 + 128
+    d = np.full((S, 2, K), -128, dtype=np.int8)
+    out = slicing.digits_gemm(d, np.ones(2), d, np.ones(2))
+    x = -2.0 * sum(2.0 ** (-8 * s) for s in range(S))                 # 2^-6 sum_s (-128) 2^-8s
+    dropped = sum((2 * S - 1 - l) * 2.0 ** (2 - 8 * l) for l in range(S, 2 * S - 1))
+    np.testing.assert_allclose(out, K * (x * x - dropped), rtol=1e-15)

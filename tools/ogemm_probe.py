@@ -12,7 +12,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-STAGES = ['slice', 'one', 'k1024', 'big', 'ragged', 's8', 'apply', 'time_apply', 'time_parts', 'syrk', 'time_syrk']
+STAGES = ['i8_peak', 'slice', 'one', 'k1024', 'big', 'ragged', 's8', 'apply', 'time_apply', 'time_parts', 'syrk', 'time_syrk']
 
 
 def run(stage):
@@ -43,7 +43,7 @@ def run(stage):
         for s in range(S):
             for t in range(S - s):
                 P = As[s].double() @ Bs[t].double().T          # exact: |P| < 2^53
-                acc += P * 2.0 ** (-7 * (s + t + 2))
+                acc += P * 2.0 ** (-8 * (s + t) - 12)
         return sa[:, None] * sb[None, :] * acc
 
     def gemm_case(name, M, N, K, S=7):
@@ -66,19 +66,28 @@ def run(stage):
             res['ref_00'] = [float(v) for v in refd[0, :4]]
         print(json.dumps(res), flush=True)
 
-    if stage == 'slice':
+    if stage == 'i8_peak':
+        import ctypes
+        lib = _cabi.require_cuda()
+        secs = float(os.environ.get('VT_PEAK_SECS', '1.0'))
+        for n in (64, 128, 192, 256):
+            tops, clk = ctypes.c_double(), ctypes.c_double()
+            check(lib.vt_i8_peak_probe(secs, n, ctypes.byref(tops), ctypes.byref(clk), stream()))
+            print(json.dumps({'stage': stage, 'n_tile': n, 'seconds': secs, 'int8_tops': tops.value,
+                              'sm_clocks_per_128x64x32': clk.value}), flush=True)
+    elif stage == 'slice':
         X = rnd(300, 102) * torch.exp(3 * rnd(300, 1))
         X[7] = 0.0
-        for S in (7, 8):
+        for S in (6, 7):
             d, sc = ops.ozaki_slice(X, S)
             rec = torch.zeros_like(X)
             for s in range(S):
-                rec += d[s, :, :102].double() * 2.0 ** (-7 * (s + 1))
+                rec += d[s, :, :102].double() * 2.0 ** (-8 * s - 6)
             rec *= sc[:, None]
             rowmax = X.abs().max(dim=1).values.clamp_min(1e-300)
             print(json.dumps({'stage': stage, 'S': S, 'max_digit': int(d.abs().max()), 'pad_zero': bool((d[:, :, 102:] == 0).all()),
                               'resid_rel_rowmax': float(((X - rec).abs().max(dim=1).values / rowmax).max()),
-                              'bound': 2.0 ** (-7 * S), 'scale_pow2': bool((torch.frexp(sc)[0] == 0.5).all()),
+                              'bound': 2.0 ** (-(8 * S - 1)), 'scale_pow2': bool((torch.frexp(sc)[0] == 0.5).all()),
                               'scale_covers': bool((sc >= X.abs().max(dim=1).values).all())}), flush=True)
     elif stage == 'one':
         gemm_case(stage, 128, 64, 128)
@@ -92,7 +101,7 @@ def run(stage):
         gemm_case(stage, 200, 300, 100)
         gemm_case(stage + '_k1000', 130, 515, 1000)
     elif stage == 's8':
-        gemm_case(stage, 512, 512, 1024, S=8)
+        gemm_case(stage, 512, 512, 1024, S=5)
         gemm_case(stage + '_s6', 512, 512, 1024, S=6)
     elif stage in ('apply', 'time_apply'):
         D = 1024
@@ -116,7 +125,7 @@ def run(stage):
     elif stage == 'time_parts':
         lib = _cabi.require_cuda()
         D = 1024
-        for S in (6, 7, 8):
+        for S in (5, 6, 7):
             nchunk = 37888
             X = ops.synth_design(7, 0, nchunk, D, dev)
             Hinv = rnd(D, D)

@@ -28,6 +28,7 @@ SIGNATURES = {
     'vt_launch_count': (_I64, []),
     'vt_device_info': (_I, [_c.POINTER(_I)] * 3),
     'vt_fp64_peak_probe': (_I, [_D, _c.POINTER(_D), _P]),
+    'vt_i8_peak_probe': (_I, [_D, _I, _c.POINTER(_D), _c.POINTER(_D), _P]),
     'vt_dgemm_workspace_bytes': (_SZ, [_I, _I, _I, _I, _I]),
     'vt_dgemm': (_I, [_I, _I, _I, _D, _P, _I64, _I, _P, _I64, _I, _D, _P, _I64, _P, _P, _P, _I, _I, _I, _P, _SZ, _P]),
     'vt_syrk_workspace_bytes': (_SZ, [_I64, _I]),

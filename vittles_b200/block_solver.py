@@ -13,6 +13,9 @@ from . import ops
 from ._arrays import to_device, kind_of, as_kind
 
 
+BLOCK_MAXM = 32          # csrc/blockchol.cuh: one block per warp / CTA out of shared memory
+
+
 class BlockArrowSolver:
     def __init__(self, h, overwrite=False):
         self.h = h

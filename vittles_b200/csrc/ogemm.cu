@@ -82,7 +82,7 @@ __device__ __forceinline__ OUnit o_decode(const OKernelArgs& a, long u) {
 // tensor peak.  Measured (ncu, S = 8): tensor pipe 90 % active at 65 clk per
 // 128x64x32 MMA - the N = 64 tile that the S accumulators force is bound by the
 // shared-memory operand reads (6 KB per MMA), not by L2 or by issue.
-template <int S>
+template <int S, bool STACK>
 __global__ void __launch_bounds__(O_THREADS, 1)
 ogemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const OKernelArgs a) {
   constexpr int B_BUF_BYTES = OCfg<S>::B_BUF_BYTES;
@@ -143,8 +143,7 @@ ogemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     // ==================================================== MMA issuer ====
     if (elect_one()) {
       // instruction descriptor: D = S32, A = B = signed INT8, both K-major, N >> 3, M >> 4
-      constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OBN >> 3) << 17) |
-                                 ((uint32_t)(OBM >> 4) << 24);
+      constexpr uint32_t idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OBM >> 4) << 24);
       // K-major 128-byte-swizzled operand: descriptor hi half = SBO 1024 B | version 1 | SWIZZLE_128B (constant),
       // lo half = (address >> 4) | LBO 16 B << 16; one UMMA_K = 32 B = +2, one B slice = 8 KB = +512.
       const uint64_t d0 = umma_desc(0u, 16u, 1024u, 2u);
@@ -165,13 +164,37 @@ ogemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             mbar_wait_(afull(as), aph);
             tc_fence_after();
             const uint32_t a_lo0 = desc_lo0 + ((sA0 + as * A_TILE_BYTES) >> 4);
+            if constexpr (STACK) {
+              // Slice s of A meets slices 0 .. S-1-s of B, whose tiles are CONTIGUOUS in the B box (64 rows of
+              // 128 bytes each), and product (s, t) belongs to accumulator s + t = columns 64 (s + t): one
+              // tcgen05.mma with N = 64 (S - s) (cut at 256) does them all and reads the A tile once instead of
+              // S - s times - 10 instructions and 96 KB of shared-memory operand reads per k-step for S = 7
+              // instead of 28 instructions and 168 KB (the N = 64 form is bound by those reads).
+              const int NTOT = OBN * (S - s);
+              const int NPART = (NTOT + 255) / 256;
+              const int NFIRST = ((NTOT / NPART) + 63) / 64 * 64;           // balanced parts, multiples of 64
 #pragma unroll
-            for (int t = 0; t < S - s; ++t) {
-              const uint32_t tmem_d = tmem_base + (uint32_t)((s + t) * OBN);
+              for (int pn = 0; pn < NPART; ++pn) {
+                const int c0 = pn * NFIRST;
+                const int n = (pn == NPART - 1) ? NTOT - c0 : NFIRST;
+                const uint32_t idesc = idesc0 | ((uint32_t)(n >> 3) << 17);
+                const uint32_t tmem_d = tmem_base + (uint32_t)(s * OBN + c0);
+                const uint32_t b_lo = b_lo0 + (uint32_t)((c0 / OBN) * (B_TILE_BYTES >> 4));
 #pragma unroll
-              for (int kk = 0; kk < OBK / O_UMMA_K; ++kk)
-                umma_i8_lohi(tmem_d, a_lo0 + 2u * kk, desc_hi, b_lo0 + (uint32_t)(t * (B_TILE_BYTES >> 4)) + 2u * kk, desc_hi,
-                             idesc, (s == 0 && kk == 0) ? first : 1u);
+                for (int kk = 0; kk < OBK / O_UMMA_K; ++kk)
+                  umma_i8_lohi(tmem_d, a_lo0 + 2u * kk, desc_hi, b_lo + 2u * kk, desc_hi, idesc,
+                               (s == 0 && kk == 0) ? first : 1u);
+              }
+            } else {
+              constexpr uint32_t idesc = idesc0 | ((uint32_t)(OBN >> 3) << 17);
+#pragma unroll
+              for (int t = 0; t < S - s; ++t) {
+                const uint32_t tmem_d = tmem_base + (uint32_t)((s + t) * OBN);
+#pragma unroll
+                for (int kk = 0; kk < OBK / O_UMMA_K; ++kk)
+                  umma_i8_lohi(tmem_d, a_lo0 + 2u * kk, desc_hi, b_lo0 + (uint32_t)(t * (B_TILE_BYTES >> 4)) + 2u * kk,
+                               desc_hi, idesc, (s == 0 && kk == 0) ? first : 1u);
+              }
             }
             umma_commit(aempty(as));
             if (++as == A_RING) { as = 0; aph ^= 1u; }
@@ -188,8 +211,9 @@ ogemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     const int quarter = warp & 3;
     const int row_local = quarter * 32 + lane;
     uint32_t tph = 0;
-    const double w_hi = 1.0 / 268435456.0;                        // 2^-28: accumulators 0..2 combined as P0 2^14 + P1 2^7 + P2
-    const double w_lo = exp2(-7.0 * (double)(S + 1));             // accumulators 3..S-1 combined with P_{S-1} at weight 1
+    // x / sigma = 2^-6 sum_s d_s 2^-8s  ->  a . b = sigma tau 2^-12 sum_l 2^-8l P_l (P_l: accumulator l = s + t)
+    const double w_hi = exp2(-12.0 - 16.0);                       // accumulators 0..2 combined as P0 2^16 + P1 2^8 + P2
+    const double w_lo = exp2(-12.0 - 8.0 * (double)(S - 1));      // accumulators 3..S-1 combined with P_{S-1} at weight 1
     for (long u = blockIdx.x; u < a.units; u += gridDim.x) {
       const OUnit U = o_decode(a, u);
       if (U.nkb == 0) continue;
@@ -212,10 +236,10 @@ ogemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           tmem_wait_ld();
           if (g < 3) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) hi[j] = hi[j] * 128 + (long long)(int)v[j];
+            for (int j = 0; j < 16; ++j) hi[j] = hi[j] * 256 + (long long)(int)v[j];
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) lo[j] = lo[j] * 128 + (long long)(int)v[j];
+            for (int j = 0; j < 16; ++j) lo[j] = lo[j] * 256 + (long long)(int)v[j];
           }
         }
         if (grow < a.M) {
@@ -253,43 +277,47 @@ ogemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
-// Digit s of the fixed-point value q = trunc(x 2^(7S) / sigma) (|q| < 2^(7S) <= 2^56) is the 7-bit field of |q|
-// at bit 7 (S-1-s), with the sign of q - truncation toward zero of x / sigma at every digit.  The scaling by a
-// power of two and the truncations are exact and the fields are integer shifts and masks.  Four values at
-// once: |q| is held as its low four digits (28 bits) and the rest, each digit is then a 32-bit shift + mask,
-// the sign one multiply, and PRMT packs the four int8 digits of slice `sl` (0 = most significant of
-// `nslices`) into one word (byte j = value j).
+// Balanced base-256 digits.  q = rint(x 2^(8S-2) / sigma) (|q| <= 2^(8S-2) <= 2^54) is written as
+// q = sum_p d_p 256^p with every d_p in [-128, 127]: with the bias B = sum_p 128 256^p the ordinary bytes e_p of
+// u = q + B are d_p + 128, i.e. the digits are the bytes of u ^ B.  An int8 digit then carries a full 8 bits
+// (sign-magnitude digits carry 7), so 7 slices hold 54 bits and S (S + 1) / 2 = 28 digit products do the work
+// of the 36 that 8 sign-magnitude slices need.  The scaling by a power of two is exact, rint rounds once, and
+// q is assembled from two 32-bit conversions (hi = rint(t 2^-24), lo = rint(t - hi 2^24), both exact; a 64-bit
+// conversion is emulated in software and made the slicers instruction bound).  Slice `sl` (0 = most significant
+// of `nslices`) of four values is packed with PRMT into one word (byte j = value j).
 // (oracle/slicing.py is the CPU model; tests/test_gpu_ozaki.py compares digit for digit.)
 struct Fixed4 {
-  uint32_t lo[4], hi[4];
-  int sgn[4];
+  uint32_t lo[4], hi[4];       // the two halves of u ^ B
 };
-// t = x * 2^(7 (S-4)) / sigma (|t| < 2^28 for S <= 8): the integer part of |t| holds the digits above the low
-// four, its fraction times 2^28 the low four.  Only 32-bit conversions (a 64-bit one is emulated in software
-// and made the slicers instruction bound); every step is exact in FP64.
-__device__ __forceinline__ void fixed4_set(Fixed4& f, int j, double t) {
-  const double a = fabs(t);
-  const uint32_t hi = __double2uint_rz(a);
-  f.hi[j] = hi;
-  f.lo[j] = __double2uint_rz((a - (double)hi) * 268435456.0) & 0x0FFFFFFFu;
-  f.sgn[j] = t < 0.0 ? -1 : 1;
+__device__ __forceinline__ unsigned long long digit_bias(int nslices) {
+  return 0x8080808080808080ULL >> (8 * (8 - nslices));
+}
+// t = x * 2^(8S-2) / sigma, |t| <= 2^(8S-2)
+__device__ __forceinline__ void fixed4_set(Fixed4& f, int j, double t, unsigned long long bias) {
+  const int hi = __double2int_rn(t * (1.0 / 16777216.0));          // |hi| <= 2^30
+  const int lo = __double2int_rn(fma(-(double)hi, 16777216.0, t)); // |lo| <= 2^23, exact remainder
+  const long long q = ((long long)hi << 24) + (long long)lo;
+  const unsigned long long u = ((unsigned long long)q + bias) ^ bias;
+  f.lo[j] = (uint32_t)u;
+  f.hi[j] = (uint32_t)(u >> 32);
 }
 __device__ __forceinline__ uint32_t fixed4_digits(const Fixed4& f, int sl, int nslices) {
-  const int pos = nslices - 1 - sl;              // digit position from the least significant one
-  int d[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const uint32_t w = pos < 4 ? f.lo[j] : f.hi[j];
-    const int sh = 7 * (pos < 4 ? pos : pos - 4);
-    d[j] = (int)((w >> sh) & 127u) * f.sgn[j];
+  const int pos = nslices - 1 - sl;              // byte position from the least significant one
+  const uint32_t sel = (uint32_t)(pos & 3);
+  const uint32_t pick = sel | ((4u + sel) << 4);   // PRMT: byte `sel` of the first source, byte `sel` of the second
+  uint32_t p01, p23;
+  if (pos < 4) {
+    p01 = __byte_perm(f.lo[0], f.lo[1], pick);
+    p23 = __byte_perm(f.lo[2], f.lo[3], pick);
+  } else {
+    p01 = __byte_perm(f.hi[0], f.hi[1], pick);
+    p23 = __byte_perm(f.hi[2], f.hi[3], pick);
   }
-  const uint32_t p01 = __byte_perm((uint32_t)d[0], (uint32_t)d[1], 0x0040);
-  const uint32_t p23 = __byte_perm((uint32_t)d[2], (uint32_t)d[3], 0x0040);
   return __byte_perm(p01, p23, 0x5410);
 }
 
-// One warp per row: row maximum -> power-of-two scale -> S truncated base-128 digits,
-// so that sum_s d_s 2^{-7s} reproduces x / sigma to 7 S bits.
+// One warp per row: row maximum -> power-of-two scale -> S balanced base-256 digits,
+// so that 2^-6 sum_s d_s 2^{-8s} reproduces x / sigma to 8 S - 2 bits (round to nearest).
 __global__ void __launch_bounds__(256) ozaki_slice_kernel(const double* __restrict__ X, long ldx, long rows, int cols,
                                                           int8_t* __restrict__ out, long ldo, long slice_stride,
                                                           int nslices, double* __restrict__ scale_out,
@@ -311,14 +339,15 @@ __global__ void __launch_bounds__(256) ozaki_slice_kernel(const double* __restri
     finite = __all_sync(0xffffffffu, finite);
     int e = 0;
     if (finite && m > 0.0) (void)frexp(m, &e);         // m = f 2^e, f in [0.5, 1)  ->  |x| 2^-e < 1
-    const double up = ldexp(1.0, 7 * (nslices - 4) - e);   // |x * up| < 2^(7 (S-4)): digits above / below the binary point
+    const double up = ldexp(1.0, 8 * nslices - 2 - e);     // |x * up| <= 2^(8S-2)
+    const unsigned long long bias = digit_bias(nslices);
     // a row with an Inf or NaN gets a NaN scale: every result that touches it is NaN, as in FP64 arithmetic
     if (lane == 0) scale_out[r] = finite ? ldexp(1.0, e) * (fold ? fold[r] : 1.0) : __longlong_as_double(0x7ff8000000000000LL);
     // four consecutive elements per lane: one 4-byte store per slice, 128 contiguous bytes per warp
     for (int c0 = lane * 4; c0 < ldo; c0 += 128) {
       Fixed4 f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) fixed4_set(f, j, (c0 + j < cols) ? xr[c0 + j] * up : 0.0);
+      for (int j = 0; j < 4; ++j) fixed4_set(f, j, (c0 + j < cols) ? xr[c0 + j] * up : 0.0, bias);
       for (int s = 0; s < nslices; ++s)
         *reinterpret_cast<uint32_t*>(out + (long)s * slice_stride + r * ldo + c0) = fixed4_digits(f, s, nslices);
     }
@@ -404,7 +433,8 @@ __global__ void __launch_bounds__(256) ozaki_slice_t_kernel(const double* __rest
       if (finite && m > 0.0) (void)frexp(m, &e);
       if (n0 == 0 && warp == 0) scale_out[i] = finite ? ldexp(1.0, e) : m;   // NaN scale: row and column i of H become NaN
     }
-    const double up = ldexp(1.0, 7 * (nslices - 4) - e);
+    const double up = ldexp(1.0, 8 * nslices - 2 - e);
+    const unsigned long long bias = digit_bias(nslices);
     // four consecutive observations per step: their digits of one slice pack into one 32-bit shared-memory store
 #pragma unroll 2
     for (int rr = 4 * warp; rr < ST_OBS; rr += 32) {
@@ -414,7 +444,7 @@ __global__ void __launch_bounds__(256) ozaki_slice_t_kernel(const double* __rest
         const long n = n0 + rr + j;
         double t = 0.0;
         if (n < rows && i < cols) t = (X[n * ldx + i] * sq[n]) * up;   // |x sq| < 2^e (same products as colmax)
-        fixed4_set(f, j, t);
+        fixed4_set(f, j, t, bias);
       }
       for (int sl = 0; sl < nslices; ++sl)
         *reinterpret_cast<uint32_t*>(sm + (sl * ST_FEAT + lane) * ST_PITCH + rr) = fixed4_digits(f, sl, nslices);
@@ -468,9 +498,18 @@ int make_slice_map(CUtensorMap* map, const int8_t* base, long rows, int K, long 
   return VT_OK;
 }
 
-template <int S>
+// VT_OGEMM_STACK=0 selects the one-product-per-instruction issue loop (N = 64) for A/B measurements.
+bool ogemm_stacked() {
+  static const bool on = [] {
+    const char* e = getenv("VT_OGEMM_STACK");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+template <int S, bool STACK>
 int launch_s(const CUtensorMap& mA, const CUtensorMap& mB, const OKernelArgs& a, cudaStream_t stream) {
-  auto kern = ogemm_kernel<S>;
+  auto kern = ogemm_kernel<S, STACK>;
   VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, OCfg<S>::SMEM_BYTES));
   VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   const long slots = num_sms();
@@ -570,7 +609,7 @@ int ogemm_launch_opts(int M, int N, int K, const int8_t* A, long lda, long a_sli
   VT_REQUIRE(M >= 0 && N >= 0 && K >= 1, "ogemm: bad dimensions");
   if (M == 0 || N == 0) return VT_OK;
   VT_REQUIRE(A && B && C, "ogemm: null operand");
-  VT_REQUIRE(nslices >= 6 && nslices <= OZAKI_MAX_SLICES, "ogemm: 6, 7 or 8 slices are instantiated");
+  VT_REQUIRE(nslices >= OZAKI_MIN_SLICES && nslices <= OZAKI_MAX_SLICES, "ogemm: 5, 6 or 7 slices are instantiated");
   VT_REQUIRE(o.parts >= 1 && (K + o.parts - 1) / o.parts <= OZAKI_MAX_K + OBK,
              "ogemm: K = %d in %d part(s) exceeds %d per part (INT32 accumulation bound)", K, o.parts, OZAKI_MAX_K);
   VT_REQUIRE(lda % 16 == 0 && ldb % 16 == 0 && a_slice_stride % 16 == 0 && b_slice_stride % 16 == 0,
@@ -603,13 +642,119 @@ int ogemm_launch_opts(int M, int N, int K, const int8_t* A, long lda, long a_sli
   a.alpha = alpha;
   a.rowscale = rowscale; a.colscale = colscale;
   a.c_vec = (ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(C) % 32 == 0) && (o.part_stride % 4 == 0);
+  const bool stk = ogemm_stacked();
   switch (nslices) {
-    case 6: return launch_s<6>(mA, mB, a, stream);
-    case 7: return launch_s<7>(mA, mB, a, stream);
-    default: return launch_s<8>(mA, mB, a, stream);
+    case 5: return stk ? launch_s<5, true>(mA, mB, a, stream) : launch_s<5, false>(mA, mB, a, stream);
+    case 6: return stk ? launch_s<6, true>(mA, mB, a, stream) : launch_s<6, false>(mA, mB, a, stream);
+    default: return stk ? launch_s<7, true>(mA, mB, a, stream) : launch_s<7, false>(mA, mB, a, stream);
   }
 }
 }  // namespace
+
+// ---- INT8 tensor peak probe -------------------------------------------------
+// One CTA per SM; one elected thread issues tcgen05.mma.kind::i8 (M = 128, K = 32) on resident shared-memory
+// operands (pseudo-random bytes: the power drawn depends on the data) with no loads in the loop.  Per iteration
+// the four k-steps of one 128-byte k-block against 448 accumulator columns, as instructions of N = n_tile
+// (64 ... 256): the same MACs per iteration whatever the instruction shape.
+namespace {
+constexpr int PROBE_COLS = 448;
+__global__ void __launch_bounds__(128, 1) i8_peak_kernel(int n_tile, long iters, long long* clocks_out) {
+  extern __shared__ uint8_t pk_smem_raw[];
+  const uint32_t base = (smem_u32(pk_smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = base, sB = base + A_TILE_BYTES, bars = sB + PROBE_COLS * OBK, slot = bars + 64;
+  uint8_t* gen = pk_smem_raw + (base - smem_u32(pk_smem_raw));
+  for (int i = threadIdx.x; i < (A_TILE_BYTES + PROBE_COLS * OBK) / 4; i += blockDim.x) {
+    uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 40503u;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    reinterpret_cast<uint32_t*>(gen)[i] = h;
+  }
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init_(bars + 8u * i, 1);
+    fence_barrier_init_();
+  }
+  if (warp == 1) tmem_alloc<512>(slot);
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");      // generic-proxy fills -> tensor-core reads
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<uint32_t*>(pk_smem_raw + (slot - smem_u32(pk_smem_raw)));
+  if (warp == 1 && elect_one()) {
+    constexpr uint32_t idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OBM >> 4) << 24);
+    const uint64_t d0 = umma_desc(0u, 16u, 1024u, 2u);
+    const uint32_t desc_hi = (uint32_t)(d0 >> 32), desc_lo0 = (uint32_t)d0;
+    const uint32_t a_lo0 = desc_lo0 + (sA >> 4), b_lo0 = desc_lo0 + (sB >> 4);
+    const long long t0 = clock64();
+    uint32_t ph[4] = {0, 0, 0, 0};
+    for (long it = 0; it < iters; ++it) {
+      const int r = (int)(it & 3);
+      if (it >= 4) { mbar_wait_(bars + 8u * r, ph[r]); ph[r] ^= 1u; }     // at most four iterations in flight
+      for (int c0 = 0; c0 < PROBE_COLS; c0 += n_tile) {
+        const int n = (PROBE_COLS - c0 < n_tile) ? PROBE_COLS - c0 : n_tile;
+        const uint32_t idesc = idesc0 | ((uint32_t)(n >> 3) << 17);
+#pragma unroll
+        for (int kk = 0; kk < OBK / O_UMMA_K; ++kk)
+          umma_i8_lohi(tmem_base + (uint32_t)c0, a_lo0 + 2u * kk, desc_hi, b_lo0 + (uint32_t)(c0 * (OBK >> 4)) + 2u * kk,
+                       desc_hi, idesc, 1u);
+      }
+      umma_commit(bars + 8u * r);
+    }
+    for (long it = (iters > 4 ? iters - 4 : 0); it < iters; ++it) {
+      const int r = (int)(it & 3);
+      mbar_wait_(bars + 8u * r, ph[r]);
+      ph[r] ^= 1u;
+    }
+    if (blockIdx.x == 0) clocks_out[0] = clock64() - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+}  // namespace
+
+int i8_peak_probe(double seconds, int n_tile, double* tops, double* clocks_per_mma64, cudaStream_t stream) {
+  VT_REQUIRE(tops && seconds > 0 && n_tile >= 16 && n_tile <= 256 && n_tile % 16 == 0, "i8_peak_probe: bad arguments");
+  long long* clk = nullptr;
+  VT_CUDA(cudaMalloc(&clk, 8));
+  cudaEvent_t e0, e1;
+  VT_CUDA(cudaEventCreate(&e0));
+  VT_CUDA(cudaEventCreate(&e1));
+  const int smem = A_TILE_BYTES + PROBE_COLS * OBK + 1024 + 256;
+  VT_CUDA(cudaFuncSetAttribute(i8_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int grid = num_sms();
+  auto run = [&](long iters, float* ms) -> int {
+    VT_CUDA(cudaEventRecord(e0, stream));
+    i8_peak_kernel<<<grid, 128, smem, stream>>>(n_tile, iters, clk);
+    VT_LAUNCH_CHECK();
+    VT_CUDA(cudaEventRecord(e1, stream));
+    VT_CUDA(cudaEventSynchronize(e1));
+    VT_CUDA(cudaEventElapsedTime(ms, e0, e1));
+    return VT_OK;
+  };
+  const long iters0 = 2000;
+  float ms = 0.f;
+  int st = run(iters0, &ms);
+  if (st == VT_OK) st = run(iters0, &ms);
+  long iters = iters0;
+  if (st == VT_OK) {
+    const double want = seconds * 1e3 / (ms > 1e-3f ? ms : 1e-3f) * (double)iters0;
+    iters = want > 4e9 ? 4000000000L : (long)want;
+    if (iters < iters0) iters = iters0;
+    st = run(iters, &ms);
+  }
+  if (st == VT_OK) {
+    *tops = 2.0 * OBM * PROBE_COLS * OBK * (double)grid * (double)iters / (ms * 1e-3) / 1e12;
+    if (clocks_per_mma64) {
+      long long c = 0;
+      VT_CUDA(cudaMemcpy(&c, clk, 8, cudaMemcpyDeviceToHost));
+      *clocks_per_mma64 = (double)c / ((double)iters * (PROBE_COLS / 64) * (OBK / O_UMMA_K));
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(clk);
+  return st;
+}
 
 int ogemm_launch(int M, int N, int K, const int8_t* A, long lda, long a_slice_stride, const int8_t* B, long ldb,
                  long b_slice_stride, int nslices, double alpha, const double* rowscale, const double* colscale, double* C,
@@ -630,7 +775,7 @@ int ij_apply_ozaki(const double* Hinv, long ldh, const double* X, long ldx, long
                    double* S, long lds, int nslices, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   VT_REQUIRE(Hinv && X && resid && S && workspace, "ij_apply_ozaki: null pointer");
   VT_REQUIRE(D >= 1 && D <= OZAKI_MAX_K && N >= 0 && ldh >= D && ldx >= D && lds >= N, "ij_apply_ozaki: bad shape");
-  VT_REQUIRE(nslices >= 6 && nslices <= OZAKI_MAX_SLICES, "ij_apply_ozaki: 6, 7 or 8 slices");
+  VT_REQUIRE(nslices >= OZAKI_MIN_SLICES && nslices <= OZAKI_MAX_SLICES, "ij_apply_ozaki: 5, 6 or 7 slices");
   VT_REQUIRE(workspace_bytes >= ij_apply_ozaki_workspace_bytes(N, D, nslices), "ij_apply_ozaki: workspace too small");
   if (N == 0) return VT_OK;
   const long ld = (D + 15) / 16 * 16;
@@ -721,7 +866,7 @@ int syrk_ozaki(const double* X, long ldx, long N, int D, const double* s, double
                void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   VT_REQUIRE(X && H && workspace, "syrk_ozaki: null pointer");
   VT_REQUIRE(D >= 1 && N >= 1 && ldx >= D && ldh >= D, "syrk_ozaki: bad shape");
-  VT_REQUIRE(nslices >= 6 && nslices <= OZAKI_MAX_SLICES, "syrk_ozaki: 6, 7 or 8 slices");
+  VT_REQUIRE(nslices >= OZAKI_MIN_SLICES && nslices <= OZAKI_MAX_SLICES, "syrk_ozaki: 5, 6 or 7 slices");
   VT_REQUIRE(workspace_bytes >= syrk_ozaki_workspace_bytes(N, D, nslices), "syrk_ozaki: workspace too small");
   const SyrkPlan p = syrk_plan(N, D, nslices);
   char* w = static_cast<char*>(workspace);

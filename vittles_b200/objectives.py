@@ -28,6 +28,12 @@ class StructuredObjective:
     """Marker base class: objectives with ``vt_*`` kernel hooks."""
     group = None
 
+    @property
+    def device(self):
+        """The GPU that holds this objective's data (parameters are placed there, whatever device is current)."""
+        X = getattr(self, 'X', None)
+        return X.device if isinstance(X, torch.Tensor) else None
+
     def _allreduce(self, t):
         if self.group is not None and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
@@ -339,10 +345,10 @@ class GMMVBObjective(StructuredObjective):
         m, rho = self._split(x)
         out = ops.gmm_blocks(self.X, m, rho, self.log_pi, want_blocks=False, want_cross=False)
         r = out['r']
-        # d f / d m_k = sum_n r_nk (m_k - x_n) + prior_prec m_k
+        # d f / d m_k = sum_n r_nk (m_k - x_n) + prior_prec m_k: only the data term is summed over the ranks
         rsum = r.sum(0)
-        gm = rsum[:, None] * m - ops.gemm(r, self.X, 'KS', 'KS') + self.prior_prec * m
-        return torch.cat([self._allreduce(gm).reshape(-1), out['grad_rho'].reshape(-1)])
+        gm = self._allreduce(rsum[:, None] * m - ops.gemm(r, self.X, 'KS', 'KS')) + self.prior_prec * m
+        return torch.cat([gm.reshape(-1), out['grad_rho'].reshape(-1)])
 
     def vt_hessian(self, x):
         raise NotImplementedError('the dense Hessian of a GMM-VB objective is never formed; use SparseBlockHessian')

@@ -14,11 +14,12 @@ from . import _cabi
 from ._cabi import check, ptr, stream
 
 _workspaces = {}
-# digits per operand of the 'f64_ozaki' engine: 8 -> 56 bits >= the 53-bit significand; 7 -> 49 bits, ~22 % faster,
-# still inside rtol 1e-8 on well-scaled data but close to the 1e-12 max|ref| floor (VT_OZAKI_SLICES=6|7|8 overrides)
-OZAKI_SLICES = int(os.environ.get('VT_OZAKI_SLICES', '8'))
-if OZAKI_SLICES not in (6, 7, 8):
-    raise ValueError('VT_OZAKI_SLICES must be 6, 7 or 8')
+# balanced base-256 digits per operand of the 'f64_ozaki' engine: 7 -> 54 bits of the row scale (FP64 DMMA results
+# reproduced to ~1e-14 of max|C|, 28 digit products); 6 -> 46 bits (~1e-12: on the edge of the parity floor, 21
+# products); 5 -> 38 bits (VT_OZAKI_SLICES=5|6|7 overrides)
+OZAKI_SLICES = int(os.environ.get('VT_OZAKI_SLICES', '7'))
+if OZAKI_SLICES not in (5, 6, 7):
+    raise ValueError('VT_OZAKI_SLICES must be 5, 6 or 7')
 
 
 def _ws(key, nbytes, device):
@@ -48,6 +49,16 @@ def _mat(t, name):
     _f64(t, name)
     if t.dim() != 2 or t.stride(1) != 1:
         raise ValueError('{} must be a row-major 2-d tensor (unit stride in the last dimension)'.format(name))
+    return t
+
+
+def _vec_opt(t, name, n=None):
+    """Optional per-row / per-column vector: packed float64 on the device (None stays None)."""
+    if t is None:
+        return None
+    t = _f64(t, name).reshape(-1).contiguous()
+    if n is not None and t.numel() < n:
+        raise ValueError('{} has {} entries, expected {}'.format(name, t.numel(), n))
     return t
 
 
@@ -87,11 +98,16 @@ def gemm(A, B, amode='KC', bmode='KC', alpha=1.0, beta=0.0, out=None, M=None, N=
     bm = _cabi.OP_KC if bmode == 'KC' else _cabi.OP_KS
     m, ka = (A.shape if am == _cabi.OP_KC else A.shape[::-1])
     n, kb = (B.shape if bm == _cabi.OP_KC else B.shape[::-1])
+    if K is None:
+        if ka != kb:
+            raise ValueError('gemm: inner dimensions differ ({} vs {})'.format(ka, kb))
+        K = ka
     M = m if M is None else M
     N = n if N is None else N
-    K = ka if K is None else K
-    if ka != kb and K is None:
-        raise ValueError('gemm: inner dimensions differ ({} vs {})'.format(ka, kb))
+    if not (0 <= M <= m and 0 <= N <= n and 0 <= K <= min(ka, kb)):
+        raise ValueError('gemm: M, N, K = {}, {}, {} exceed the operands ({} x {} and {} x {})'.format(M, N, K, m, ka, n, kb))
+    kscale, colscale, rowscale = (_vec_opt(kscale, 'kscale', K), _vec_opt(colscale, 'colscale', N),
+                                  _vec_opt(rowscale, 'rowscale', M))
     if out is None:
         if beta != 0.0:
             raise ValueError('gemm: beta != 0 needs `out`')
@@ -148,7 +164,7 @@ def tf32_gemm(A, B, amode='KC', bmode='KC', alpha=1.0, precision='tf32', colscal
 # ------------------------------------- INT8 error-free slicing (optional) ----
 def ozaki_slice(X, nslices=OZAKI_SLICES, fold=None):
     """(digits (nslices, rows, ld) int8, scale (rows,) float64) of a float64 matrix:
-    X[r, k] = scale[r] * sum_s digits[s, r, k] 2^{-7 (s + 1)} up to 2^{-7 nslices}
+    X[r, k] = scale[r] * 2^-6 sum_s digits[s, r, k] 2^{-8 s} up to scale[r] 2^{-(8 nslices - 1)}
     (``fold`` multiplies the returned scale row by row)."""
     lib = _cabi.require_cuda()
     _mat(X, 'X')
@@ -241,7 +257,7 @@ def glm_stats(X, theta, y, w=None, family='logistic', l2=0.0, want_grad=True, wa
     grad = torch.empty(D, dtype=torch.float64, device=dev) if want_grad else None
     ws, wsb = _ws('glm', lib.vt_glm_workspace_bytes(D), dev)
     check(lib.vt_glm_stats(ptr(X), _ld(X), N, D, ptr(_f64(theta, 'theta').contiguous()), ptr(_f64(y, 'y')),
-                           ptr(w), _cabi.GLM_FAMILIES[family], ptr(z), ptr(resid), ptr(s), ptr(grad), float(l2),
+                           ptr(_vec_opt(w, 'w', N)), _cabi.GLM_FAMILIES[family], ptr(z), ptr(resid), ptr(s), ptr(grad), float(l2),
                            ptr(ws), wsb, stream()))
     return z, resid, s, grad
 
@@ -270,7 +286,7 @@ def glm_dirderiv(X, z, dirs, w=None, family='logistic', out=None):
     if out is None:
         out = torch.empty(D, dtype=torch.float64, device=X.device)
     ws, wsb = _ws('glm', lib.vt_glm_dirderiv_workspace_bytes(N, D), X.device)
-    check(lib.vt_glm_dirderiv(ptr(X), _ld(X), N, D, ptr(_f64(z, 'z')), ptr(w), _cabi.GLM_FAMILIES[family],
+    check(lib.vt_glm_dirderiv(ptr(X), _ld(X), N, D, ptr(_f64(z, 'z')), ptr(_vec_opt(w, 'w', N)), _cabi.GLM_FAMILIES[family],
                               ptr(dirs), dirs.shape[0], ptr(out), ptr(ws), wsb, stream()))
     return out
 
@@ -486,3 +502,45 @@ def gmm_blocks(X, m, rho, log_pi, want_blocks=True, want_cross=True):
                             ptr(_f64(log_pi, 'log_pi').contiguous()), ptr(blocks), ptr(cross), ptr(rmat),
                             ptr(grad_rho), ptr(obj), stream()))
     return dict(blocks=blocks, cross=cross, r=rmat, grad_rho=grad_rho, obj_terms=obj)
+
+
+# ---------------------------------------------------------- device scoping ----
+# The library launches on the CURRENT device's current stream (its workspace queries and SM count use
+# cudaGetDevice).  Every wrapper above therefore runs with the device of its first CUDA tensor argument
+# (or its `device` argument) made current, so tensors on a non-current GPU are handled on their own device
+# and stream instead of faulting or racing.
+def _device_of(args, kwargs):
+    for a in list(args) + list(kwargs.values()):
+        if isinstance(a, torch.Tensor) and a.is_cuda:
+            return a.device
+        if isinstance(a, CholeskyFactor):
+            return a.L.device
+        if isinstance(a, torch.device) and a.type == 'cuda':
+            return a
+        if isinstance(a, (tuple, list)):
+            for b in a:
+                if isinstance(b, torch.Tensor) and b.is_cuda:
+                    return b.device
+    return None
+
+
+def _device_scoped(fn):
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = _device_of(args, kwargs)
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
+
+
+for _name in ('gemm', 'tf32_convert', 'tf32_gemm', 'ozaki_slice', 'ozaki_gemm', 'syrk_weighted', 'glm_stats', 'glm_hvp',
+              'glm_dirderiv', 'potrf', 'ij_apply', 'gemv', 'cg_init', 'cg_update_p', 'cg_update_xr', 'synth_design',
+              'synth_theta', 'synth_bernoulli', 'block_potrf', 'block_trsm', 'block_solve', 'tall_gemv', 'tall_colsum',
+              'gmm_blocks'):
+    globals()[_name] = _device_scoped(globals()[_name])
+CholeskyFactor.solve = _device_scoped(CholeskyFactor.solve)
+del _name

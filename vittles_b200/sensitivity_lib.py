@@ -111,6 +111,15 @@ class EstimatingEquationLinearApproximation:
                           validate_solution=validate_solution, solution_tol=solution_tol)
 
     # -- hooks overridden by the structured path --------------------------
+    def _home_device(self, value=None):
+        """Where the parameters live: a structured objective's own GPU, else the device of a CUDA input, else the
+        current device."""
+        obj = getattr(self, '_objective_fun', None)
+        dev = getattr(obj, 'device', None)
+        if dev is None and isinstance(value, torch.Tensor) and value.is_cuda:
+            dev = value.device
+        return dev
+
     def _eval_estimating_equation(self, x, h):
         return self._estimating_equation(x, h)
 
@@ -123,7 +132,7 @@ class EstimatingEquationLinearApproximation:
         """Reference: ``sensitivity_lib.py:192-226``."""
         self._kind = kind_of(input_val0)
         self._hyper_kind = kind_of(hyper_val0)
-        self._input_val0 = to_device(deepcopy(input_val0)).reshape(-1)
+        self._input_val0 = to_device(deepcopy(input_val0), self._home_device(input_val0)).reshape(-1)
         self._hyper_val0 = to_device(deepcopy(hyper_val0), self._input_val0.device).reshape(-1)
 
         if validate_solution:
@@ -215,7 +224,7 @@ class HyperparameterSensitivityLinearApproximation(EstimatingEquationLinearAppro
         shape check, then ALWAYS the Cholesky solver."""
         self._stats = None
         if hessian_at_opt is None:
-            theta = to_device(opt_par_value).reshape(-1)
+            theta = to_device(opt_par_value, self._home_device(opt_par_value)).reshape(-1)
             lam = to_device(hyper_par_value, theta.device).reshape(-1)
             if self._structured and hasattr(self._objective_fun, 'vt_stats_and_hessian'):
                 self._stats, self._hess0 = self._objective_fun.vt_stats_and_hessian(theta, lam)

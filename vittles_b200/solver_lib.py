@@ -114,7 +114,7 @@ def get_cg_solver(mat_times_vec, dim, cg_opts={}):
     callback = opts.get('callback', None)
 
     def solve(v):
-        if getattr(v, 'ndim', 1) == 2 and v.shape[1] != 1:
+        if getattr(v, 'ndim', 1) == 2:                       # any 2-d v, (dim, 1) included, is a matrix: shape preserved
             if v.shape[0] != dim:
                 raise ValueError('right-hand side has shape {}, expected ({}, K)'.format(tuple(v.shape), dim))
             vd = to_device(v)

@@ -11,6 +11,13 @@ natural block-arrow layout
 (:class:`BlockArrowHessian`), which converts to a scipy COO / dense matrix on
 request and is what ``solver_lib.get_cholesky_solver`` factorises with the
 batched block-Cholesky + Schur-complement kernels.
+
+Return-type change with respect to the reference: ``get_block_hessian`` /
+``get_global_hessian`` / ``get_hessian`` return a :class:`BlockArrowHessian`, not a
+``scipy.sparse.coo_matrix`` (a COO matrix of 4e8 entries on the host is exactly
+what this build avoids).  ``.tocoo()`` gives the reference's type, ``.todense()`` /
+``.toarray()`` / ``@`` work as on a scipy matrix, and ``scipy.sparse.issparse`` is
+False - ``solver_lib.get_cholesky_solver`` dispatches on the class itself.
 """
 import numpy as np
 import scipy.sparse
@@ -137,13 +144,66 @@ class BlockArrowHessian:
     def todense(self):
         return np.asarray(self.tocoo().todense())
 
+    def to_dense_tensor(self):
+        """The (d, d) matrix as a float64 tensor on the device (small problems only)."""
+        d = self.shape[0]
+        sa, gi = self.sparsity_array, self.global_inds
+        G, M = sa.shape
+        out = torch.zeros((d, d), dtype=torch.float64, device=sa.device)
+        if self.blocks is not None:
+            out.index_put_((sa[:, :, None].expand(G, M, M), sa[:, None, :].expand(G, M, M)), self.blocks, accumulate=True)
+        Dg = gi.numel()
+        if self.cross is not None and Dg > 0:
+            r = sa[:, :, None].expand(G, M, Dg)
+            c = gi[None, None, :].expand(G, M, Dg)
+            out.index_put_((r, c), self.cross, accumulate=True)
+            out.index_put_((c, r), self.cross, accumulate=True)
+        if self.hgg is not None and Dg > 0:
+            out.index_put_((gi[:, None].expand(Dg, Dg), gi[None, :].expand(Dg, Dg)), self.hgg, accumulate=True)
+        return out
+
     def toarray(self):
         return self.todense()
+
+    def matvec(self, v):
+        """``H @ v`` for a (d,) or (d, K) array, without densifying."""
+        kind = kind_of(v)
+        x = to_device(v, self.sparsity_array.device)
+        vec = x.dim() == 1
+        x2 = x.reshape(self.shape[0], -1)
+        sa, gi = self.sparsity_array, self.global_inds
+        out = torch.zeros_like(x2)
+        xl = x2[sa]                                        # (G, M, K)
+        if self.blocks is not None:
+            out[sa] += torch.einsum('gij,gjk->gik', self.blocks, xl)
+        if gi.numel() > 0:
+            xg = x2[gi]                                    # (Dg, K)
+            if self.cross is not None:
+                out[sa] += torch.einsum('gij,jk->gik', self.cross, xg)
+                out[gi] += torch.einsum('gij,gik->jk', self.cross, xl)
+            if self.hgg is not None:
+                out[gi] += self.hgg @ xg
+        return as_kind(out.reshape(-1) if vec else out, kind)
+
+    def __matmul__(self, v):
+        return self.matvec(v)
+
+    def dot(self, v):
+        return self.matvec(v)
 
     def get_solver(self):
         """``solve(v) -> H^{-1} v`` by batched block Cholesky and a dense Schur
         complement on the global block."""
-        from .block_solver import BlockArrowSolver
+        from .block_solver import BlockArrowSolver, BLOCK_MAXM
+        if self.sparsity_array.shape[1] > BLOCK_MAXM:
+            # the batched kernels keep one block per warp / CTA in shared memory (M <= 32); wider blocks go the way
+            # the reference's SuperLU goes - a general factorisation - here the dense GPU Cholesky
+            if self.shape[0] > 32768:
+                raise ValueError('block-arrow solver: blocks of size {} exceed the batched kernels\' limit of {} and '
+                                 'the matrix (dimension {}) is too large to densify'.format(
+                                     self.sparsity_array.shape[1], BLOCK_MAXM, self.shape[0]))
+            from .solver_lib import get_dense_cholesky_solver
+            return get_dense_cholesky_solver(self.to_dense_tensor())
         return BlockArrowSolver(self).solve
 
 

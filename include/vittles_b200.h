@@ -58,10 +58,10 @@ int vt_device_info(int* sm_count, int* cc_major, int* cc_minor);
 int vt_fp64_peak_probe(double seconds, double* tflops, void* stream);
 /* Runs a bare tcgen05.mma.kind::i8 loop (M = 128, N = n_tile in 16..256, K = 32;
  * operands resident in shared memory, no loads) for about `seconds` and
- * returns the achieved dense INT8 TOP/s and the SM clocks per 128 x 64 x 32
- * instruction-equivalent (may be NULL): the roofline denominator of the
+ * returns the achieved dense INT8 TOP/s and the SM clocks per 128 x n_tile x 32
+ * instruction (may be NULL): the roofline denominator of the
  * error-free-slicing engine (MEASURED_PEAKS.json has no INT8 entry).  Synchronous. */
-int vt_i8_peak_probe(double seconds, int n_tile, double* tops, double* clocks_per_mma64, void* stream);
+int vt_i8_peak_probe(double seconds, int n_tile, double* tops, double* clocks_per_mma, void* stream);
 
 /* ---- FP64 tensor-core GEMM engine ---------------------------------------
  * C(m,n) = alpha * rowscale[m] * colscale[n] * sum_k kscale[k] A(m,k) B(n,k) + beta * C(m,n)

@@ -49,8 +49,8 @@ def reconstruct(digits, scale):
 
 def sliced_gemm(a, b, nslices):
     """A @ B.T the way the engine evaluates it: exact INT64 digit products, products with the same s + t share an
-    accumulator, accumulators 0..2 and 3..S-1 are combined in two INT64 words and one FP64 FMA per element
-    (``ogemm_kernel`` epilogue), then the row / column scales."""
+    accumulator, the accumulators are combined by Horner's rule in FP64 (``ogemm_kernel`` epilogue), then the
+    row / column scales."""
     da, sa = slice_rows(a, nslices)
     db, sb = slice_rows(b, nslices)
     return digits_gemm(da, sa, db, sb)
@@ -65,15 +65,20 @@ def digits_gemm(da, sa, db, sb):
             groups[s + t] += da[s].astype(np.int64) @ db[t].astype(np.int64).T
     for g in groups:
         assert np.max(np.abs(g)) < 2 ** 31, 'INT32 accumulator bound violated (K too large)'
-    hi = np.zeros_like(groups[0])
-    lo = np.zeros_like(groups[0])
-    for g in range(nslices):
-        if g < 3:
-            hi = hi * 256 + groups[g]
-        else:
-            lo = lo * 256 + groups[g]
-    val = lo.astype(np.float64) * 2.0 ** (-12 - 8 * (nslices - 1)) + hi.astype(np.float64) * 2.0 ** -28
-    return sa[:, None] * sb[None, :] * val
+    # Horner's rule in float64 from the least significant accumulator over PAIRS of accumulators (P_l 256 + P_{l+1}
+    # is an exact integer below 2^41), as the epilogue of ``ogemm_kernel`` does it (t * 2^-k is exact, so numpy's
+    # multiply-add equals the kernel's fused multiply-add bit for bit)
+    def pair(g):
+        return (groups[g] * 256 + groups[g + 1]).astype(np.float64)
+    if nslices % 2 == 1:
+        g = nslices - 3
+        val = groups[nslices - 1].astype(np.float64) * (1.0 / 256.0) + pair(g)
+    else:
+        g = nslices - 2
+        val = pair(g)
+    for g in range(g - 2, -1, -2):
+        val = val * (1.0 / 65536.0) + pair(g)
+    return (sa[:, None] * 2.0 ** -20) * sb[None, :] * val
 
 
 def error_bound(k, nslices):

@@ -70,11 +70,11 @@ def run(stage):
         import ctypes
         lib = _cabi.require_cuda()
         secs = float(os.environ.get('VT_PEAK_SECS', '1.0'))
-        for n in (64, 128, 192, 256):
+        for n in [int(v) for v in os.environ.get('VT_PEAK_N', '64,128,192,256').split(',')]:
             tops, clk = ctypes.c_double(), ctypes.c_double()
             check(lib.vt_i8_peak_probe(secs, n, ctypes.byref(tops), ctypes.byref(clk), stream()))
             print(json.dumps({'stage': stage, 'n_tile': n, 'seconds': secs, 'int8_tops': tops.value,
-                              'sm_clocks_per_128x64x32': clk.value}), flush=True)
+                              'sm_clocks_per_mma': clk.value}), flush=True)
     elif stage == 'slice':
         X = rnd(300, 102) * torch.exp(3 * rnd(300, 1))
         X[7] = 0.0
@@ -105,7 +105,7 @@ def run(stage):
         gemm_case(stage + '_s6', 512, 512, 1024, S=6)
     elif stage in ('apply', 'time_apply'):
         D = 1024
-        N = 20000 if stage == 'apply' else 1000000
+        N = int(os.environ.get('VT_APPLY_N', '20000')) if stage == 'apply' else 1000000
         X = ops.synth_design(7, 0, N, D, dev)
         Hm = rnd(D, D)
         Hinv = torch.linalg.inv(Hm @ Hm.T / D + 0.05 * torch.eye(D, device=dev, dtype=torch.float64)).contiguous()
@@ -143,6 +143,43 @@ def run(stage):
                               'slice_gb_per_s': nchunk * D * (8 + S) / ms_slice / 1e6, 'ms_gemm': ms_gemm,
                               'fp64_equiv_tflops': 2.0 * D * D * nchunk / ms_gemm / 1e9,
                               'int8_tops': 2.0 * D * D * nchunk * pairs / ms_gemm / 1e9}), flush=True)
+    elif stage == 'timing':
+        # VT_OGEMM_TIMING=1 must be set: where the MMA-issuing thread waits (clocks, mean over CTAs)
+        import ctypes
+        lib = _cabi.require_cuda()
+        D, S, nchunk = 1024, 7, 37888
+        X = ops.synth_design(7, 0, nchunk, D, dev)
+        Hinv = rnd(D, D)
+        Bs, sb = ops.ozaki_slice(X, S)
+        As, sa = ops.ozaki_slice(Hinv, S)
+        out = torch.empty((D, nchunk), dtype=torch.float64, device=dev)
+
+        def gemm_only():
+            check(lib.vt_ozaki_gemm(D, nchunk, D, ptr(As), As.stride(1), As.stride(0), ptr(Bs), Bs.stride(1),
+                                    Bs.stride(0), S, -1.0, ptr(sa), ptr(sb), ptr(out), nchunk, stream()))
+        buf = (ctypes.c_ulonglong * 8)()
+        gemm_only(); torch.cuda.synchronize()
+        lib.vt_debug_ogemm_timing.restype = ctypes.c_int
+        lib.vt_debug_ogemm_timing(buf)
+        ms = timed(gemm_only, reps=1)
+        rc = lib.vt_debug_ogemm_timing(buf)
+        n = max(1, buf[4])
+        print(json.dumps({'stage': stage, 'rc': rc, 'ms': ms, 'launches_x_ctas': buf[4], 'clk_total': buf[0] / n,
+                          'clk_wait_accum': buf[1] / n, 'clk_wait_B': buf[2] / n, 'clk_wait_A': buf[3] / n,
+                          'tiles_per_cta': 8 * (nchunk // 64) / 148}), flush=True)
+        # the whole apply (fused slicing of the next chunk unless VT_OZAKI_FUSE=0)
+        N = 20 * nchunk
+        Xb = ops.synth_design(7, 0, N, D, dev)
+        resid = rnd(N)
+        outb = ops.ij_apply(Hinv, Xb, resid, precision='f64_ozaki')
+        torch.cuda.synchronize()
+        lib.vt_debug_ogemm_timing(buf)
+        ms = timed(lambda: ops.ij_apply(Hinv, Xb, resid, out=outb, precision='f64_ozaki'), reps=1)
+        lib.vt_debug_ogemm_timing(buf)
+        n, nc = max(1, buf[4]), max(1, buf[6])
+        print(json.dumps({'stage': stage + '_apply', 'chunks': 20, 'ms': ms, 'mma_clk_total_per_launch': buf[0] / n,
+                          'clk_wait_accum': buf[1] / n, 'clk_wait_B': buf[2] / n, 'clk_wait_A': buf[3] / n,
+                          'converter_clk_per_launch': buf[5] / nc, 'converter_warps': buf[6]}), flush=True)
     elif stage in ('syrk', 'time_syrk'):
         D = 1024
         for N in ((777, 50000) if stage == 'syrk' else (1000000,)):

@@ -89,8 +89,8 @@ int vt_fp64_peak_probe(double seconds, double* tflops, void* stream) {
   return st;
 }
 
-int vt_i8_peak_probe(double seconds, int n_tile, double* tops, double* clocks_per_mma64, void* stream) {
-  return i8_peak_probe(seconds, n_tile, tops, clocks_per_mma64, S(stream));
+int vt_i8_peak_probe(double seconds, int n_tile, double* tops, double* clocks_per_mma, void* stream) {
+  return i8_peak_probe(seconds, n_tile, tops, clocks_per_mma, S(stream));
 }
 
 size_t vt_dgemm_workspace_bytes(int M, int N, int K, int lower, int tile) {

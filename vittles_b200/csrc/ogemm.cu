@@ -13,7 +13,10 @@ constexpr int OBM = 128;               // tile rows (TMEM lanes)
 constexpr int OBN = 64;                // tile columns: S accumulators x 64 columns <= 512 TMEM columns
 constexpr int OBK = 128;               // int8 elements (bytes) per k-block = one 128-byte swizzle row
 constexpr int O_UMMA_K = 32;           // k per tcgen05.mma.kind::i8
-constexpr int O_THREADS = 192;         // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int O_THREADS = 576;         // warps 0-7: slice the rows of the NEXT chunk while this one is multiplied,
+                                       // warps 8-15: epilogue, warp 16: TMA producer, warp 17: MMA issuer + TMEM owner
+constexpr int O_EPI_WARPS = 8, O_CONV_WARPS = 8;
+constexpr int W_EPI0 = O_CONV_WARPS, W_TMA = O_CONV_WARPS + O_EPI_WARPS, W_MMA = W_TMA + 1;   // W_EPI0 % 4 == 0 (TMEM quarters)
 constexpr int A_TILE_BYTES = OBM * OBK;        // 16 KB: one slice of the A tile for one k-block
 constexpr int B_TILE_BYTES = OBN * OBK;        //  8 KB: one slice of the B tile for one k-block
 constexpr int A_RING = 4;                      // A slices stream through a 4-deep ring
@@ -23,6 +26,12 @@ template <int S>
 struct OCfg {
   static constexpr int B_BUF_BYTES = S * B_TILE_BYTES;
   static constexpr int SMEM_BYTES = B_BUFS * B_BUF_BYTES + A_RING * A_TILE_BYTES + 1024 + 256;
+};
+
+struct SliceJob {
+  const double* X; long ldx; long rows; int cols;
+  int8_t* out; long ldo; long slice_stride;
+  double* scale_out; const double* fold;
 };
 
 struct OKernelArgs {
@@ -38,6 +47,8 @@ struct OKernelArgs {
   const double* rowscale;
   const double* colscale;
   int c_vec;
+  SliceJob next;                // rows to slice during this launch (X == nullptr: none; cols <= 1024)
+  unsigned long long* timing;   // development aid (VT_OGEMM_TIMING=1): clocks the MMA thread waits, summed over CTAs
 };
 
 // lower: row block tm keeps the column blocks 0 .. (tm*OBM + OBM-1) / OBN
@@ -82,6 +93,140 @@ __device__ __forceinline__ OUnit o_decode(const OKernelArgs& a, long u) {
 // tensor peak.  Measured (ncu, S = 8): tensor pipe 90 % active at 65 clk per
 // 128x64x32 MMA - the N = 64 tile that the S accumulators force is bound by the
 // shared-memory operand reads (6 KB per MMA), not by L2 or by issue.
+// Balanced base-256 digits.  q = rint(x 2^(8S-2) / sigma) (|q| <= 2^(8S-2) <= 2^54) is written as
+// q = sum_p d_p 256^p with every d_p in [-128, 127]: with the bias B = sum_p 128 256^p the ordinary bytes e_p of
+// u = q + B are d_p + 128, i.e. the digits are the bytes of u ^ B.  An int8 digit then carries a full 8 bits
+// (sign-magnitude digits carry 7), so 7 slices hold 54 bits and S (S + 1) / 2 = 28 digit products do the work
+// of the 36 that 8 sign-magnitude slices need.  The scaling by a power of two is exact, rint rounds once, and
+// q is assembled from two 32-bit conversions (hi = rint(t 2^-24), lo = rint(t - hi 2^24), both exact; a 64-bit
+// conversion is emulated in software and made the slicers instruction bound).  Slice `sl` (0 = most significant
+// of `nslices`) of four values is packed with PRMT into one word (byte j = value j).
+// (oracle/slicing.py is the CPU model; tests/test_gpu_ozaki.py compares digit for digit.)
+struct Fixed4 {
+  uint32_t lo[4], hi[4];       // the two halves of u ^ B
+};
+__host__ __device__ constexpr unsigned long long digit_bias(int nslices) {
+  return 0x8080808080808080ULL >> (8 * (8 - nslices));
+}
+// t = x * 2^(8S-2) / sigma, |t| <= 2^(8S-2).  Round-to-nearest-even through the FP64 adder: v + 1.5 2^52 holds
+// rint(v) in the low word of its significand for |v| < 2^51 (no conversion instructions: those issue at a quarter
+// of the FP64 rate).
+__device__ __forceinline__ void fixed4_set(Fixed4& f, int j, double t, unsigned long long bias) {
+  constexpr double MAGIC = 6755399441055744.0;                       // 1.5 * 2^52
+  const double mh = fma(t, 1.0 / 16777216.0, MAGIC);                // rint(t 2^-24), |.| <= 2^30
+  const int hi = __double2loint(mh);
+  const double rem = fma(-(mh - MAGIC), 16777216.0, t);             // exact, |rem| <= 2^23
+  const int lo = __double2loint(rem + MAGIC);
+  const long long q = ((long long)hi << 24) + (long long)lo;
+  const unsigned long long u = ((unsigned long long)q + bias) ^ bias;
+  f.lo[j] = (uint32_t)u;
+  f.hi[j] = (uint32_t)(u >> 32);
+}
+template <int S>
+__device__ __forceinline__ uint32_t fixed4_digits(const Fixed4& f, int sl) {
+  const int pos = S - 1 - sl;                      // byte position from the least significant one
+  const uint32_t sel = (uint32_t)(pos & 3);
+  const uint32_t pick = sel | ((4u + sel) << 4);   // PRMT: byte `sel` of the first source, byte `sel` of the second
+  uint32_t p01, p23;
+  if (pos < 4) {
+    p01 = __byte_perm(f.lo[0], f.lo[1], pick);
+    p23 = __byte_perm(f.lo[2], f.lo[3], pick);
+  } else {
+    p01 = __byte_perm(f.hi[0], f.hi[1], pick);
+    p23 = __byte_perm(f.hi[2], f.hi[3], pick);
+  }
+  return __byte_perm(p01, p23, 0x5410);
+}
+
+// One warp per row: row maximum -> power-of-two scale -> S balanced base-256 digits,
+// so that 2^-6 sum_s d_s 2^{-8s} reproduces x / sigma to 8 S - 2 bits (round to nearest).
+// Rows of at most 128 * RC elements are held in registers between the two passes (RC = 0: re-read).
+template <int S, int RC>
+__device__ __forceinline__ void slice_one_row(const SliceJob& jb, long r, int lane, bool vec) {
+  constexpr unsigned long long bias = digit_bias(S);
+  const double* xr = jb.X + r * jb.ldx;
+  const int cols = jb.cols;
+  double m = 0.0;
+  bool finite = true;                                // fmax() drops NaNs: track non-finite entries separately
+  double xv[RC > 0 ? RC : 1][4];
+  if constexpr (RC > 0) {
+#pragma unroll
+    for (int ch = 0; ch < RC; ++ch) {
+      const int c0 = ch * 128 + lane * 4;
+      if (vec && c0 + 4 <= cols) {
+        const double2 a0 = *reinterpret_cast<const double2*>(xr + c0), a1 = *reinterpret_cast<const double2*>(xr + c0 + 2);
+        xv[ch][0] = a0.x; xv[ch][1] = a0.y; xv[ch][2] = a1.x; xv[ch][3] = a1.y;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) xv[ch][j] = (c0 + j < cols) ? xr[c0 + j] : 0.0;
+      }
+    }
+#pragma unroll
+    for (int ch = 0; ch < RC; ++ch)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double v = fabs(xv[ch][j]);
+        finite = finite && (v <= 1.7976931348623157e308);
+        m = fmax(m, v);
+      }
+  } else {
+    for (int c = lane; c < cols; c += 32) {
+      const double v = fabs(xr[c]);
+      finite = finite && (v <= 1.7976931348623157e308);
+      m = fmax(m, v);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  finite = __all_sync(0xffffffffu, finite);
+  int e = 0;
+  if (finite && m > 0.0) (void)frexp(m, &e);         // m = f 2^e, f in [0.5, 1)  ->  |x| 2^-e < 1
+  const double up = ldexp(1.0, 8 * S - 2 - e);       // |x * up| <= 2^(8S-2)
+  // a row with an Inf or NaN gets a NaN scale: every result that touches it is NaN, as in FP64 arithmetic
+  if (lane == 0)
+    jb.scale_out[r] = finite ? ldexp(1.0, e) * (jb.fold ? jb.fold[r] : 1.0) : __longlong_as_double(0x7ff8000000000000LL);
+  // four consecutive elements per lane: one 4-byte store per slice, 128 contiguous bytes per warp
+  int8_t* orow = jb.out + r * jb.ldo;
+  if constexpr (RC > 0) {
+#pragma unroll
+    for (int ch = 0; ch < RC; ++ch) {
+      const int c0 = ch * 128 + lane * 4;
+      if (c0 < jb.ldo) {
+        Fixed4 f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) fixed4_set(f, j, xv[ch][j] * up, bias);
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+          *reinterpret_cast<uint32_t*>(orow + (long)s * jb.slice_stride + c0) = fixed4_digits<S>(f, s);
+      }
+    }
+  } else {
+    for (int c0 = lane * 4; c0 < jb.ldo; c0 += 128) {
+      Fixed4 f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) fixed4_set(f, j, (c0 + j < cols) ? xr[c0 + j] * up : 0.0, bias);
+#pragma unroll
+      for (int s = 0; s < S; ++s)
+        *reinterpret_cast<uint32_t*>(orow + (long)s * jb.slice_stride + c0) = fixed4_digits<S>(f, s);
+    }
+  }
+}
+
+template <int S, int RC>
+__global__ void __launch_bounds__(256) ozaki_slice_kernel(const SliceJob jb) {
+  const int lane = threadIdx.x & 31;
+  const long warp0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  const bool vec = (jb.ldx % 2 == 0) && (reinterpret_cast<uintptr_t>(jb.X) % 16 == 0);
+  for (long r = warp0; r < jb.rows; r += nwarps) slice_one_row<S, RC>(jb, r, lane, vec);
+}
+
+// Exact INT64 -> FP64 for |u| < 2^51 without a conversion instruction.
+__device__ __forceinline__ double exact_double(long long u) {
+  return __longlong_as_double(u + 0x4338000000000000LL) - 6755399441055744.0;
+}
+__device__ __forceinline__ double pair_double(int hi, int lo) { return exact_double((long long)hi * 256 + (long long)lo); }
+
 template <int S, bool STACK>
 __global__ void __launch_bounds__(O_THREADS, 1)
 ogemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const OKernelArgs a) {
@@ -100,23 +245,25 @@ ogemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   const uint32_t tmem_slot = tempty + 8u;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(og_smem_raw + (tmem_slot - smem_u32(og_smem_raw)));
 
+  // Warp roles by DESCENDING issue priority (the arbiter favours the highest warp id): W_MMA, W_TMA, the epilogue
+  // warps, and at the bottom the converter warps, which only fill idle issue slots.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) {
+  if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
     for (int i = 0; i < B_BUFS; ++i) { mbar_init_(bfull(i), 1); mbar_init_(bempty(i), 1); }
     for (int i = 0; i < A_RING; ++i) { mbar_init_(afull(i), 1); mbar_init_(aempty(i), 1); }
     mbar_init_(tfull, 1);
-    mbar_init_(tempty, 4);
+    mbar_init_(tempty, O_EPI_WARPS);
     fence_barrier_init_();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == W_MMA) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (warp == 0) {
+  if (warp == W_TMA) {
     // ================================================== TMA producer ====
     if (elect_one()) {
       int bs = 0, as = 0;
@@ -139,7 +286,7 @@ ogemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == W_MMA) {
     // ==================================================== MMA issuer ====
     if (elect_one()) {
       // instruction descriptor: D = S32, A = B = signed INT8, both K-major, N >> 3, M >> 4
@@ -150,18 +297,26 @@ ogemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       const uint32_t desc_hi = (uint32_t)(d0 >> 32), desc_lo0 = (uint32_t)d0;
       int bs = 0, as = 0;
       uint32_t bph = 0, aph = 0, tph = 0;
+      long long w_t = 0, w_b = 0, w_a = 0;
+      const long long t_begin = clock64();
       for (long u = blockIdx.x; u < a.units; u += gridDim.x) {
         const OUnit U = o_decode(a, u);
         if (U.nkb == 0) continue;              // every role skips an empty unit
+        long long c0 = clock64();
         mbar_wait_(tempty, tph ^ 1u);          // the epilogue has drained the accumulators of the previous tile
+        w_t += clock64() - c0;
         tc_fence_after();
         for (int kb = 0; kb < U.nkb; ++kb) {
+          c0 = clock64();
           mbar_wait_(bfull(bs), bph);
+          w_b += clock64() - c0;
           const uint32_t b_lo0 = desc_lo0 + ((sB0 + bs * B_BUF_BYTES) >> 4);
           const uint32_t first = kb == 0 ? 0u : 1u;
 #pragma unroll
           for (int s = 0; s < S; ++s) {
+            c0 = clock64();
             mbar_wait_(afull(as), aph);
+            w_a += clock64() - c0;
             tc_fence_after();
             const uint32_t a_lo0 = desc_lo0 + ((sA0 + as * A_TILE_BYTES) >> 4);
             if constexpr (STACK) {
@@ -170,6 +325,8 @@ ogemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
               // tcgen05.mma with N = 64 (S - s) (cut at 256) does them all and reads the A tile once instead of
               // S - s times - 10 instructions and 96 KB of shared-memory operand reads per k-step for S = 7
               // instead of 28 instructions and 168 KB (the N = 64 form is bound by those reads).
+              // (measured, bare issue loop: an instruction of N columns costs max(N / 2, 34 + 0.36 N) clocks - 128 for
+              // N = 256, 101 for 192, 80 for 128, 57 for 64 - so 448 columns go as 256 + 192, 384 as 192 + 192, ...)
               const int NTOT = OBN * (S - s);
               const int NPART = (NTOT + 255) / 256;
               const int NFIRST = ((NTOT / NPART) + 63) / 64 * 64;           // balanced parts, multiples of 64
@@ -205,62 +362,78 @@ ogemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         umma_commit(tfull);
         tph ^= 1u;
       }
+      if (a.timing) {
+        atomicAdd(a.timing + 0, (unsigned long long)(clock64() - t_begin));
+        atomicAdd(a.timing + 1, (unsigned long long)w_t);
+        atomicAdd(a.timing + 2, (unsigned long long)w_b);
+        atomicAdd(a.timing + 3, (unsigned long long)w_a);
+        atomicAdd(a.timing + 4, 1ULL);
+      }
     }
-  } else {
+  } else if (warp >= W_EPI0) {
     // ====================================================== epilogue ====
-    const int quarter = warp & 3;
+    // Eight warps: warp w reads TMEM lanes 32 (w % 4) .. + 31 (the quarter a warp may address) and the column half
+    // (w - 2) / 4 of every accumulator.  sum_l P_l 2^-8l is evaluated by Horner's rule in FP64 from the least
+    // significant accumulator: every P_l is an exact double and each FMA rounds at 2^-53 of a partial sum that is
+    // 2^-8l of the leading terms - far below the 2^-54 sigma tau truncation of the digits themselves.
+    const int ew = warp - W_EPI0;
+    const int quarter = warp & 3, chalf = ew >> 2;
     const int row_local = quarter * 32 + lane;
     uint32_t tph = 0;
-    // x / sigma = 2^-6 sum_s d_s 2^-8s  ->  a . b = sigma tau 2^-12 sum_l 2^-8l P_l (P_l: accumulator l = s + t)
-    const double w_hi = exp2(-12.0 - 16.0);                       // accumulators 0..2 combined as P0 2^16 + P1 2^8 + P2
-    const double w_lo = exp2(-12.0 - 8.0 * (double)(S - 1));      // accumulators 3..S-1 combined with P_{S-1} at weight 1
     for (long u = blockIdx.x; u < a.units; u += gridDim.x) {
       const OUnit U = o_decode(a, u);
       if (U.nkb == 0) continue;
       const int m0 = U.m0, n0 = U.n0;
       const int grow = m0 + row_local;
       double* Cpart = a.C + (long)U.part * a.part_stride;
+      // a . b = sigma tau 2^-12 sum_l 2^-8l P_l, and the Horner sum below carries a factor 256
+      const double rs = (grow < a.M) ? a.alpha * (a.rowscale ? a.rowscale[grow] : 1.0) * (1.0 / 1048576.0) : 0.0;
+      // lane j keeps the scale of column j of this warp's 32 columns (fetched before the accumulators are
+      // awaited: a global load behind the TMEM wait would sit on the critical path of every strip)
+      const int ccol = n0 + chalf * (OBN / 2) + lane;
+      const double cs_lane = (a.colscale && ccol < a.N) ? a.colscale[ccol] : 1.0;
       mbar_wait_(tfull, tph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-      const double rs = (grow < a.M) ? a.alpha * (a.rowscale ? a.rowscale[grow] : 1.0) : 0.0;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(chalf * (OBN / 2));
 #pragma unroll 1
-      for (int c = 0; c < OBN; c += 16) {
-        long long hi[16], lo[16];
+      for (int c = 0; c < OBN / 2; c += 8) {
+        uint32_t v[S][8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) hi[j] = lo[j] = 0;
+        for (int g = 0; g < S; ++g) tmem_ld8(taddr + (uint32_t)(g * OBN + c), v[g]);
+        tmem_wait_ld();
+        double out[8];
 #pragma unroll
-        for (int g = 0; g < S; ++g) {
-          uint32_t v[16];
-          tmem_ld16(taddr + (uint32_t)(g * OBN + c), v);
-          tmem_wait_ld();
-          if (g < 3) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) hi[j] = hi[j] * 256 + (long long)(int)v[j];
+        for (int j = 0; j < 8; ++j) {
+          // Horner from the least significant accumulator over PAIRS of accumulators: P_l 256 + P_{l+1} is formed
+          // in INT64 and converted exactly by adding it to the bit pattern of 1.5 2^52 (an I2F.F64 issues at a
+          // quarter of the DADD / DFMA rate and one per accumulator made the conversions the epilogue's bound)
+          double t;
+          int g;
+          if constexpr (S % 2 == 1) {
+            t = exact_double((long long)(int)v[S - 1][j]);
+            g = S - 3;
+            t = fma(t, 1.0 / 256.0, pair_double((int)v[g][j], (int)v[g + 1][j]));
           } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) lo[j] = lo[j] * 256 + (long long)(int)v[j];
+            g = S - 2;
+            t = pair_double((int)v[g][j], (int)v[g + 1][j]);
           }
+#pragma unroll
+          for (g -= 2; g >= 0; g -= 2) t = fma(t, 1.0 / 65536.0, pair_double((int)v[g][j], (int)v[g + 1][j]));
+          out[j] = t * (rs * __shfl_sync(0xffffffffu, cs_lane, c + j));      // t = 256 sum_l P_l 2^-8l
         }
         if (grow < a.M) {
-          const int gcol = n0 + c;
-          double out[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const double cs = (a.colscale && gcol + j < a.N) ? a.colscale[gcol + j] : 1.0;
-            out[j] = rs * cs * fma((double)lo[j], w_lo, (double)hi[j] * w_hi);
-          }
+          const int gcol = n0 + chalf * (OBN / 2) + c;
           double* cp = Cpart + (long)grow * a.ldc + gcol;
-          if (a.c_vec && gcol + 16 <= a.N) {
+          if (a.c_vec && gcol + 8 <= a.N) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
+            for (int j = 0; j < 8; j += 4) {
               double o0 = 0.0, o1 = 0.0, o2 = 0.0, o3 = 0.0;
               if (a.accumulate) ld_global_v4(cp + j, o0, o1, o2, o3);
               st_global_v4(cp + j, o0 + out[j], o1 + out[j + 1], o2 + out[j + 2], o3 + out[j + 3]);
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
+            for (int j = 0; j < 8; ++j)
               if (gcol + j < a.N) cp[j] = (a.accumulate ? cp[j] : 0.0) + out[j];
           }
         }
@@ -270,88 +443,25 @@ ogemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       if (lane == 0) mbar_arrive_(tempty);
       tph ^= 1u;
     }
+  } else if (a.next.X != nullptr) {
+    // ===================================================== converters ====
+    // The digits of the next chunk's rows, written while the tensor pipe works on this chunk: the slicing pass
+    // (HBM bound on its own: 8 bytes read, S written per element) disappears behind the GEMM.  Four consecutive
+    // rows per CTA and step, one warp per row, the row held in registers between the maximum and the digits.
+    const int cw = warp;
+    const bool vec = (a.next.ldx % 2 == 0) && (reinterpret_cast<uintptr_t>(a.next.X) % 16 == 0);
+    const long long t_begin = clock64();
+    for (long r = (long)blockIdx.x * O_CONV_WARPS + cw; r < a.next.rows; r += (long)gridDim.x * O_CONV_WARPS)
+      slice_one_row<S, 8>(a.next, r, lane, vec);
+    if (a.timing && lane == 0) {
+      atomicAdd(a.timing + 5, (unsigned long long)(clock64() - t_begin));
+      atomicAdd(a.timing + 6, 1ULL);
+    }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
-}
-
-// Balanced base-256 digits.  q = rint(x 2^(8S-2) / sigma) (|q| <= 2^(8S-2) <= 2^54) is written as
-// q = sum_p d_p 256^p with every d_p in [-128, 127]: with the bias B = sum_p 128 256^p the ordinary bytes e_p of
-// u = q + B are d_p + 128, i.e. the digits are the bytes of u ^ B.  An int8 digit then carries a full 8 bits
-// (sign-magnitude digits carry 7), so 7 slices hold 54 bits and S (S + 1) / 2 = 28 digit products do the work
-// of the 36 that 8 sign-magnitude slices need.  The scaling by a power of two is exact, rint rounds once, and
-// q is assembled from two 32-bit conversions (hi = rint(t 2^-24), lo = rint(t - hi 2^24), both exact; a 64-bit
-// conversion is emulated in software and made the slicers instruction bound).  Slice `sl` (0 = most significant
-// of `nslices`) of four values is packed with PRMT into one word (byte j = value j).
-// (oracle/slicing.py is the CPU model; tests/test_gpu_ozaki.py compares digit for digit.)
-struct Fixed4 {
-  uint32_t lo[4], hi[4];       // the two halves of u ^ B
-};
-__device__ __forceinline__ unsigned long long digit_bias(int nslices) {
-  return 0x8080808080808080ULL >> (8 * (8 - nslices));
-}
-// t = x * 2^(8S-2) / sigma, |t| <= 2^(8S-2)
-__device__ __forceinline__ void fixed4_set(Fixed4& f, int j, double t, unsigned long long bias) {
-  const int hi = __double2int_rn(t * (1.0 / 16777216.0));          // |hi| <= 2^30
-  const int lo = __double2int_rn(fma(-(double)hi, 16777216.0, t)); // |lo| <= 2^23, exact remainder
-  const long long q = ((long long)hi << 24) + (long long)lo;
-  const unsigned long long u = ((unsigned long long)q + bias) ^ bias;
-  f.lo[j] = (uint32_t)u;
-  f.hi[j] = (uint32_t)(u >> 32);
-}
-__device__ __forceinline__ uint32_t fixed4_digits(const Fixed4& f, int sl, int nslices) {
-  const int pos = nslices - 1 - sl;              // byte position from the least significant one
-  const uint32_t sel = (uint32_t)(pos & 3);
-  const uint32_t pick = sel | ((4u + sel) << 4);   // PRMT: byte `sel` of the first source, byte `sel` of the second
-  uint32_t p01, p23;
-  if (pos < 4) {
-    p01 = __byte_perm(f.lo[0], f.lo[1], pick);
-    p23 = __byte_perm(f.lo[2], f.lo[3], pick);
-  } else {
-    p01 = __byte_perm(f.hi[0], f.hi[1], pick);
-    p23 = __byte_perm(f.hi[2], f.hi[3], pick);
-  }
-  return __byte_perm(p01, p23, 0x5410);
-}
-
-// One warp per row: row maximum -> power-of-two scale -> S balanced base-256 digits,
-// so that 2^-6 sum_s d_s 2^{-8s} reproduces x / sigma to 8 S - 2 bits (round to nearest).
-__global__ void __launch_bounds__(256) ozaki_slice_kernel(const double* __restrict__ X, long ldx, long rows, int cols,
-                                                          int8_t* __restrict__ out, long ldo, long slice_stride,
-                                                          int nslices, double* __restrict__ scale_out,
-                                                          const double* __restrict__ fold) {
-  const int lane = threadIdx.x & 31;
-  const long warp0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
-  for (long r = warp0; r < rows; r += nwarps) {
-    const double* xr = X + r * ldx;
-    double m = 0.0;
-    bool finite = true;                                // fmax() drops NaNs: track non-finite entries separately
-    for (int c = lane; c < cols; c += 32) {
-      const double v = fabs(xr[c]);
-      finite = finite && (v <= 1.7976931348623157e308);
-      m = fmax(m, v);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-    finite = __all_sync(0xffffffffu, finite);
-    int e = 0;
-    if (finite && m > 0.0) (void)frexp(m, &e);         // m = f 2^e, f in [0.5, 1)  ->  |x| 2^-e < 1
-    const double up = ldexp(1.0, 8 * nslices - 2 - e);     // |x * up| <= 2^(8S-2)
-    const unsigned long long bias = digit_bias(nslices);
-    // a row with an Inf or NaN gets a NaN scale: every result that touches it is NaN, as in FP64 arithmetic
-    if (lane == 0) scale_out[r] = finite ? ldexp(1.0, e) * (fold ? fold[r] : 1.0) : __longlong_as_double(0x7ff8000000000000LL);
-    // four consecutive elements per lane: one 4-byte store per slice, 128 contiguous bytes per warp
-    for (int c0 = lane * 4; c0 < ldo; c0 += 128) {
-      Fixed4 f;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) fixed4_set(f, j, (c0 + j < cols) ? xr[c0 + j] * up : 0.0, bias);
-      for (int s = 0; s < nslices; ++s)
-        *reinterpret_cast<uint32_t*>(out + (long)s * slice_stride + r * ldo + c0) = fixed4_digits(f, s, nslices);
-    }
-  }
+  if (warp == W_MMA) tmem_dealloc<512>(tmem_base);
 }
 
 // ---- Hessian assembly: the contraction runs over the observations, so the digits are written
@@ -413,15 +523,17 @@ __global__ void __launch_bounds__(256) ozaki_colmax_kernel(const double* __restr
 // staged in shared memory ([slice][feature][observation], pitch 132 bytes: conflict free for the
 // feature-per-lane stores), 128-byte coalesced stores along the observations.
 constexpr int ST_OBS = 128, ST_FEAT = 32, ST_PITCH = ST_OBS + 4;
+template <int S>
 __global__ void __launch_bounds__(256) ozaki_slice_t_kernel(const double* __restrict__ X, long ldx, long rows, int cols,
                                                             const double* __restrict__ sq,
                                                             const unsigned long long* __restrict__ colmax,
                                                             int8_t* __restrict__ out, long ldo, long slice_stride,
-                                                            int nslices, double* __restrict__ scale_out) {
-  __shared__ __align__(16) int8_t sm[OZAKI_MAX_SLICES * ST_FEAT * ST_PITCH];
+                                                            double* __restrict__ scale_out) {
+  __shared__ __align__(16) int8_t sm[S * ST_FEAT * ST_PITCH];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long tiles_x = (rows + ST_OBS - 1) / ST_OBS;
   const int tiles_y = (cols + ST_FEAT - 1) / ST_FEAT;
+  constexpr unsigned long long bias = digit_bias(S);
   for (long tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
     const long n0 = (tile / tiles_y) * ST_OBS;          // feature blocks fastest: a CTA wave reads whole rows of X
     const int i0 = (int)(tile % tiles_y) * ST_FEAT;
@@ -433,29 +545,44 @@ __global__ void __launch_bounds__(256) ozaki_slice_t_kernel(const double* __rest
       if (finite && m > 0.0) (void)frexp(m, &e);
       if (n0 == 0 && warp == 0) scale_out[i] = finite ? ldexp(1.0, e) : m;   // NaN scale: row and column i of H become NaN
     }
-    const double up = ldexp(1.0, 8 * nslices - 2 - e);
-    const unsigned long long bias = digit_bias(nslices);
-    // four consecutive observations per step: their digits of one slice pack into one 32-bit shared-memory store
-#pragma unroll 2
-    for (int rr = 4 * warp; rr < ST_OBS; rr += 32) {
+    const double up = ldexp(1.0, 8 * S - 2 - e);
+    // a warp takes 16 consecutive observations of the tile (lane = feature: 256-byte coalesced reads), all 16 loads
+    // in flight at once; the digits of four observations of one slice pack into one 32-bit shared-memory store
+    const int rbase = 16 * warp;
+    double xv[16];
+    const bool full = (n0 + ST_OBS <= rows) && (i0 + ST_FEAT <= cols);
+    if (full) {
+      const double* xp = X + (n0 + rbase) * ldx + i;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) xv[q] = xp[q * ldx];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) xv[q] *= sq[n0 + rbase + q];
+    } else {
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const long n = n0 + rbase + q;
+        xv[q] = (n < rows && i < cols) ? X[n * ldx + i] * sq[n] : 0.0;     // |x sq| < 2^e (same products as colmax)
+      }
+    }
+#pragma unroll
+    for (int g4 = 0; g4 < 4; ++g4) {
       Fixed4 f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const long n = n0 + rr + j;
-        double t = 0.0;
-        if (n < rows && i < cols) t = (X[n * ldx + i] * sq[n]) * up;   // |x sq| < 2^e (same products as colmax)
-        fixed4_set(f, j, t, bias);
-      }
-      for (int sl = 0; sl < nslices; ++sl)
-        *reinterpret_cast<uint32_t*>(sm + (sl * ST_FEAT + lane) * ST_PITCH + rr) = fixed4_digits(f, sl, nslices);
+      for (int j = 0; j < 4; ++j) fixed4_set(f, j, xv[4 * g4 + j] * up, bias);
+#pragma unroll
+      for (int sl = 0; sl < S; ++sl)
+        *reinterpret_cast<uint32_t*>(sm + (sl * ST_FEAT + lane) * ST_PITCH + rbase + 4 * g4) = fixed4_digits<S>(f, sl);
     }
     __syncthreads();
     // (slice, feature) rows of 128 bytes: one warp per row, 4 bytes per lane
-    for (int row = warp; row < nslices * ST_FEAT; row += 8) {
-      const int sl = row / ST_FEAT, f = row % ST_FEAT;
-      if (i0 + f < cols && n0 + 4 * lane < ldo) {
-        const uint32_t v = *reinterpret_cast<const uint32_t*>(sm + row * ST_PITCH + 4 * lane);
-        *reinterpret_cast<uint32_t*>(out + (long)sl * slice_stride + (long)(i0 + f) * ldo + n0 + 4 * lane) = v;
+    if (n0 + 4 * lane < ldo) {
+#pragma unroll 4
+      for (int row = warp; row < S * ST_FEAT; row += 8) {
+        const int sl = row / ST_FEAT, f = row % ST_FEAT;
+        if (i0 + f < cols) {
+          const uint32_t v = *reinterpret_cast<const uint32_t*>(sm + row * ST_PITCH + 4 * lane);
+          *reinterpret_cast<uint32_t*>(out + (long)sl * slice_stride + (long)(i0 + f) * ldo + n0 + 4 * lane) = v;
+        }
       }
     }
     __syncthreads();
@@ -498,6 +625,14 @@ int make_slice_map(CUtensorMap* map, const int8_t* base, long rows, int K, long 
   return VT_OK;
 }
 
+bool ozaki_fuse_slicing() {
+  static const bool on = [] {
+    const char* e = getenv("VT_OZAKI_FUSE");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 // VT_OGEMM_STACK=0 selects the one-product-per-instruction issue loop (N = 64) for A/B measurements.
 bool ogemm_stacked() {
   static const bool on = [] {
@@ -505,6 +640,18 @@ bool ogemm_stacked() {
     return !(e && e[0] == '0');
   }();
   return on;
+}
+
+// VT_OGEMM_TIMING=1: a device buffer of 8 counters {total, wait accumulators, wait B, wait A, CTAs} that every
+// launch adds to; vt_debug_ogemm_timing() reads and clears it.
+unsigned long long* ogemm_timing_buffer() {
+  static unsigned long long* buf = [] {
+    const char* e = getenv("VT_OGEMM_TIMING");
+    unsigned long long* p = nullptr;
+    if (e && e[0] == '1' && cudaMalloc(&p, 64) == cudaSuccess) cudaMemset(p, 0, 64);
+    return p;
+  }();
+  return buf;
 }
 
 template <int S, bool STACK>
@@ -580,19 +727,40 @@ long ozaki_chunk_rows(long N, int D, int nslices) {
 
 }  // namespace
 
+unsigned long long* ogemm_timing_buffer_public() { return ogemm_timing_buffer(); }
+
 int ozaki_slice(const double* X, long ldx, long rows, int cols, int8_t* out, long ldo, long slice_stride, int nslices,
                 double* scale_out, const double* fold, cudaStream_t stream) {
   VT_REQUIRE(X && out && scale_out, "ozaki_slice: null pointer");
   VT_REQUIRE(rows >= 0 && cols >= 1 && ldx >= cols && ldo >= cols && ldo % 16 == 0, "ozaki_slice: bad shape");
-  VT_REQUIRE(nslices >= 1 && nslices <= OZAKI_MAX_SLICES && slice_stride >= rows * ldo && slice_stride % 16 == 0,
+  VT_REQUIRE(nslices >= OZAKI_MIN_SLICES && nslices <= OZAKI_MAX_SLICES && slice_stride >= rows * ldo && slice_stride % 16 == 0,
              "ozaki_slice: bad slice layout");
   VT_REQUIRE(reinterpret_cast<uintptr_t>(out) % 16 == 0, "ozaki_slice: output must be 16-byte aligned");
   if (rows == 0) return VT_OK;
-  long blocks = (rows + 7) / 8;
-  const long cap = (long)num_sms() * (ozaki_overlap() ? 4 : 8);      // overlapped: leave room for the resident GEMM CTA
+  // overlapped (VT_OZAKI_OVERLAP=1): CTAs of 4 warps, two per SM - what fits in the registers the resident GEMM CTA
+  // leaves (320 threads x 96 registers of 64 K)
+  const int bt = ozaki_overlap() ? 128 : 256;
+  long blocks = (rows + bt / 32 - 1) / (bt / 32);
+  const long cap = (long)num_sms() * (ozaki_overlap() ? 2 : 8);
   if (blocks > cap) blocks = cap;
-  ozaki_slice_kernel<<<(unsigned)blocks, 256, 0, stream>>>(X, ldx, rows, cols, out, ldo, slice_stride, nslices, scale_out,
-                                                          fold);
+  const int rc = cols <= 1024 ? (cols + 127) / 128 : 0;        // rows of up to 1024 elements stay in registers
+  const SliceJob jb{X, ldx, rows, cols, out, ldo, slice_stride, scale_out, fold};
+#define VT_SLICE_CASE(SS, RR) ozaki_slice_kernel<SS, RR><<<(unsigned)blocks, bt, 0, stream>>>(jb)
+#define VT_SLICE_S(SS)                                                           \
+  switch (rc) {                                                                  \
+    case 1: VT_SLICE_CASE(SS, 1); break;                                         \
+    case 2: VT_SLICE_CASE(SS, 2); break;                                         \
+    case 3: case 4: VT_SLICE_CASE(SS, 4); break;                                 \
+    case 5: case 6: case 7: case 8: VT_SLICE_CASE(SS, 8); break;                 \
+    default: VT_SLICE_CASE(SS, 0); break;                                        \
+  }
+  switch (nslices) {
+    case 5: VT_SLICE_S(5); break;
+    case 6: VT_SLICE_S(6); break;
+    default: VT_SLICE_S(7); break;
+  }
+#undef VT_SLICE_S
+#undef VT_SLICE_CASE
   VT_LAUNCH_CHECK();
   return VT_OK;
 }
@@ -601,6 +769,7 @@ namespace {
 struct OLaunchOpts {
   int lower = 0, parts = 1, accumulate = 0;
   long part_stride = 0;
+  SliceJob next{};              // rows sliced by the converter warps of this launch (X == nullptr: none)
 };
 
 int ogemm_launch_opts(int M, int N, int K, const int8_t* A, long lda, long a_slice_stride, const int8_t* B, long ldb,
@@ -642,6 +811,9 @@ int ogemm_launch_opts(int M, int N, int K, const int8_t* A, long lda, long a_sli
   a.alpha = alpha;
   a.rowscale = rowscale; a.colscale = colscale;
   a.c_vec = (ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(C) % 32 == 0) && (o.part_stride % 4 == 0);
+  a.next = o.next;
+  if (a.next.X) VT_REQUIRE(a.next.cols <= 1024 && a.next.ldo % 16 == 0, "ogemm: in-kernel slicing takes rows of at most 1024 elements");
+  a.timing = ogemm_timing_buffer();
   const bool stk = ogemm_stacked();
   switch (nslices) {
     case 5: return stk ? launch_s<5, true>(mA, mB, a, stream) : launch_s<5, false>(mA, mB, a, stream);
@@ -654,8 +826,7 @@ int ogemm_launch_opts(int M, int N, int K, const int8_t* A, long lda, long a_sli
 // ---- INT8 tensor peak probe -------------------------------------------------
 // One CTA per SM; one elected thread issues tcgen05.mma.kind::i8 (M = 128, K = 32) on resident shared-memory
 // operands (pseudo-random bytes: the power drawn depends on the data) with no loads in the loop.  Per iteration
-// the four k-steps of one 128-byte k-block against 448 accumulator columns, as instructions of N = n_tile
-// (64 ... 256): the same MACs per iteration whatever the instruction shape.
+// the four k-steps of one 128-byte k-block against floor(448 / n_tile) accumulators of N = n_tile columns.
 namespace {
 constexpr int PROBE_COLS = 448;
 __global__ void __launch_bounds__(128, 1) i8_peak_kernel(int n_tile, long iters, long long* clocks_out) {
@@ -689,8 +860,8 @@ __global__ void __launch_bounds__(128, 1) i8_peak_kernel(int n_tile, long iters,
     for (long it = 0; it < iters; ++it) {
       const int r = (int)(it & 3);
       if (it >= 4) { mbar_wait_(bars + 8u * r, ph[r]); ph[r] ^= 1u; }     // at most four iterations in flight
-      for (int c0 = 0; c0 < PROBE_COLS; c0 += n_tile) {
-        const int n = (PROBE_COLS - c0 < n_tile) ? PROBE_COLS - c0 : n_tile;
+      for (int c0 = 0; c0 + n_tile <= PROBE_COLS; c0 += n_tile) {       // whole instructions of N = n_tile only
+        const int n = n_tile;
         const uint32_t idesc = idesc0 | ((uint32_t)(n >> 3) << 17);
 #pragma unroll
         for (int kk = 0; kk < OBK / O_UMMA_K; ++kk)
@@ -712,7 +883,7 @@ __global__ void __launch_bounds__(128, 1) i8_peak_kernel(int n_tile, long iters,
 }
 }  // namespace
 
-int i8_peak_probe(double seconds, int n_tile, double* tops, double* clocks_per_mma64, cudaStream_t stream) {
+int i8_peak_probe(double seconds, int n_tile, double* tops, double* clocks_per_mma, cudaStream_t stream) {
   VT_REQUIRE(tops && seconds > 0 && n_tile >= 16 && n_tile <= 256 && n_tile % 16 == 0, "i8_peak_probe: bad arguments");
   long long* clk = nullptr;
   VT_CUDA(cudaMalloc(&clk, 8));
@@ -743,11 +914,12 @@ int i8_peak_probe(double seconds, int n_tile, double* tops, double* clocks_per_m
     st = run(iters, &ms);
   }
   if (st == VT_OK) {
-    *tops = 2.0 * OBM * PROBE_COLS * OBK * (double)grid * (double)iters / (ms * 1e-3) / 1e12;
-    if (clocks_per_mma64) {
+    const int per_iter = PROBE_COLS / n_tile;                  // instructions per k-step
+    *tops = 2.0 * OBM * (double)(per_iter * n_tile) * OBK * (double)grid * (double)iters / (ms * 1e-3) / 1e12;
+    if (clocks_per_mma) {
       long long c = 0;
       VT_CUDA(cudaMemcpy(&c, clk, 8, cudaMemcpyDeviceToHost));
-      *clocks_per_mma64 = (double)c / ((double)iters * (PROBE_COLS / 64) * (OBK / O_UMMA_K));
+      *clocks_per_mma = (double)c / ((double)iters * per_iter * (OBK / O_UMMA_K));
     }
   }
   cudaEventDestroy(e0);
@@ -755,6 +927,16 @@ int i8_peak_probe(double seconds, int n_tile, double* tops, double* clocks_per_m
   cudaFree(clk);
   return st;
 }
+
+}  // namespace vt
+extern "C" int vt_debug_ogemm_timing(unsigned long long* out8) {
+  unsigned long long* b = vt::ogemm_timing_buffer_public();
+  if (!b) return 1;
+  if (cudaMemcpy(out8, b, 64, cudaMemcpyDeviceToHost) != cudaSuccess) return 2;
+  cudaMemset(b, 0, 64);
+  return 0;
+}
+namespace vt {
 
 int ogemm_launch(int M, int N, int K, const int8_t* A, long lda, long a_slice_stride, const int8_t* B, long ldb,
                  long b_slice_stride, int nslices, double alpha, const double* rowscale, const double* colscale, double* C,
@@ -806,19 +988,30 @@ int ij_apply_ozaki(const double* Hinv, long ldh, const double* X, long ldx, long
   }
   st = ozaki_slice(Hinv, ldh, D, D, As, ld, (long)D * ld, nslices, sigma, nullptr, stream);
   if (st != VT_OK) return st;
+  // Chunk c + 1 is sliced by the converter warps of the GEMM of chunk c (rows of up to 1024 elements; VT_OZAKI_FUSE=0
+  // or longer rows: a separate slicing launch per chunk).
+  const bool fuse = !overlap && D <= 1024 && ozaki_fuse_slicing();
   long c = 0;
   for (long r0 = 0; r0 < N; r0 += ch, ++c) {
     const int b = (int)(c & 1);
     const long rows = (N - r0 < ch) ? N - r0 : ch;
     if (overlap && c >= 2) VT_CUDA(cudaStreamWaitEvent(L->side, L->consumed[b], 0));   // GEMM c-2 has read buffer b
-    st = ozaki_slice(X + r0 * ldx, ldx, rows, D, Bs[b], ld, ch * ld, nslices, tau[b], resid + r0, slicer);   // tau_n resid_n
-    if (st != VT_OK) return st;
+    if (!fuse || c == 0) {
+      st = ozaki_slice(X + r0 * ldx, ldx, rows, D, Bs[b], ld, ch * ld, nslices, tau[b], resid + r0, slicer);   // tau_n resid_n
+      if (st != VT_OK) return st;
+    }
     if (overlap) {
       VT_CUDA(cudaEventRecord(L->ready[b], L->side));
       VT_CUDA(cudaStreamWaitEvent(stream, L->ready[b], 0));
     }
-    st = ogemm_launch(D, (int)rows, D, As, ld, (long)D * ld, Bs[b], ld, ch * ld, nslices, -1.0, sigma, tau[b], S + r0, lds,
-                      stream);
+    OLaunchOpts o;
+    const long n0 = r0 + ch;
+    if (fuse && n0 < N) {
+      const long nrows = (N - n0 < ch) ? N - n0 : ch;
+      o.next = SliceJob{X + n0 * ldx, ldx, nrows, D, Bs[b ^ 1], ld, ch * ld, tau[b ^ 1], resid + n0};
+    }
+    st = ogemm_launch_opts(D, (int)rows, D, As, ld, (long)D * ld, Bs[b], ld, ch * ld, nslices, -1.0, sigma, tau[b], S + r0, lds,
+                           o, stream);
     if (st != VT_OK) return st;
     if (overlap) VT_CUDA(cudaEventRecord(L->consumed[b], stream));
   }
@@ -911,8 +1104,12 @@ int syrk_ozaki(const double* X, long ldx, long N, int D, const double* s, double
     if (overlap && c >= 2) VT_CUDA(cudaStreamWaitEvent(L->side, L->consumed[b], 0));
     const long tiles = ((rows + ST_OBS - 1) / ST_OBS) * ((D + ST_FEAT - 1) / ST_FEAT);
     const long cap = (long)num_sms() * (overlap ? 1 : 6);
-    ozaki_slice_t_kernel<<<(unsigned)(tiles < cap ? tiles : cap), 256, 0, slicer>>>(X + r0 * ldx, ldx, rows, D, sq + r0, cmax,
-                                                                                    Xs[b], p.ld, slice_stride, nslices, sigma);
+    const unsigned tgrid = (unsigned)(tiles < cap ? tiles : cap);
+    switch (nslices) {
+      case 5: ozaki_slice_t_kernel<5><<<tgrid, 256, 0, slicer>>>(X + r0 * ldx, ldx, rows, D, sq + r0, cmax, Xs[b], p.ld, slice_stride, sigma); break;
+      case 6: ozaki_slice_t_kernel<6><<<tgrid, 256, 0, slicer>>>(X + r0 * ldx, ldx, rows, D, sq + r0, cmax, Xs[b], p.ld, slice_stride, sigma); break;
+      default: ozaki_slice_t_kernel<7><<<tgrid, 256, 0, slicer>>>(X + r0 * ldx, ldx, rows, D, sq + r0, cmax, Xs[b], p.ld, slice_stride, sigma); break;
+    }
     VT_LAUNCH_CHECK();
     if (overlap) {
       VT_CUDA(cudaEventRecord(L->ready[b], L->side));

@@ -34,9 +34,11 @@ int ogemm_launch(int M, int N, int K, const int8_t* A, long lda, long a_slice_st
                  long b_slice_stride, int nslices, double alpha, const double* rowscale, const double* colscale, double* C,
                  long ldc, cudaStream_t stream);
 
+unsigned long long* ogemm_timing_buffer_public();   // development aid, see ogemm.cu
+
 // Bare tcgen05.mma.kind::i8 loop (no loads) for about `seconds`: achieved dense INT8 TOP/s with instructions
-// of N = n_tile, and SM clocks per 128 x 64 x 32 instruction-equivalent.  The denominator of the engine's roofline.
-int i8_peak_probe(double seconds, int n_tile, double* tops, double* clocks_per_mma64, cudaStream_t stream);
+// of N = n_tile, and SM clocks per 128 x n_tile x 32 instruction.  The denominator of the engine's roofline.
+int i8_peak_probe(double seconds, int n_tile, double* tops, double* clocks_per_mma, cudaStream_t stream);
 
 // S (D x N) = -Hinv diag(resid) X^T with FP64-grade accuracy on the INT8 tensor cores.
 size_t ij_apply_ozaki_workspace_bytes(long N, int D, int nslices);

@@ -60,13 +60,17 @@ class GLMObjective(StructuredObjective):
     ``family``: 'logistic' (b = softplus), 'poisson' (b = exp), 'gaussian'.
 
     ``precision`` selects the engine of the two contractions (Hessian assembly
-    and the H^{-1} G^T apply): 'f64' (default; FP64 DMMA, the path the rtol 1e-8
-    parity bar applies to) or the optional 'tf32' / 'tf32x3' tcgen05 path
-    (relative error about 5e-4 / 2e-5 of the operand scale; statistics,
-    factorisation and the inverse stay in FP64)."""
+    and the H^{-1} G^T apply).  The two FP64-grade engines are held to the same
+    rtol 1e-8 parity bar: 'f64' (FP64 DMMA) and 'f64_ozaki' (error-free slicing
+    on the INT8 tensor cores, ~2.5x faster at N = 1e7, D = 1024); 'auto' (the
+    default) takes the INT8 engine when N D^2 >= 1e11 and the weights are
+    non-negative, the DMMA engine otherwise (``ops.resolve_precision``).
+    Optional reduced precision: 'tf32' / 'tf32x3' (relative error about 5e-4 /
+    2e-5 of the operand scale).  Statistics, factorisation and the inverse are
+    FP64 on every engine."""
 
     def __init__(self, X, y, family='logistic', l2=0.0, device=None, group=None, stream_chunks=16,
-                 precision='f64'):
+                 precision='auto'):
         ops._split(precision)
         self.precision = precision
         self._pending, self._host_src = [], None

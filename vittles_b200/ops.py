@@ -194,14 +194,32 @@ def ozaki_gemm(A, B, alpha=1.0, nslices=OZAKI_SLICES, out=None):
 
 
 # ------------------------------------------------------- Hessian assembly ----
-PRECISIONS = {'f64': 0, 'tf32': 1, 'tf32x3': 3, 'f64_ozaki': 0}
+PRECISIONS = {'auto': 0, 'f64': 0, 'tf32': 1, 'tf32x3': 3, 'f64_ozaki': 0}
+# 'auto' (the default of the objective classes) picks between the two FP64-grade engines, which are held to the
+# same parity bar: the INT8 error-free-slicing engine once the contraction is large enough to amortise its slicing
+# passes and fill its 128 x 64 tiles (N D^2 >= 1e11, e.g. N >= 1e5 at D = 1024), the FP64 DMMA engine otherwise
+# (and whenever the weights of the Hessian are not all non-negative: the slicing engine factors out sqrt(s)).
+AUTO_OZAKI_MIN_WORK = 1e11
+AUTO_OZAKI_MIN_DIM = 128
 
 
 def _split(precision):
-    """0 for the FP64 DMMA engine, else the TF32 split (1 | 3) of the tcgen05 engine."""
+    """0 for the FP64-grade engines, else the TF32 split (1 | 3) of the tcgen05 engine."""
     if precision not in PRECISIONS:
-        raise ValueError("precision must be 'f64', 'tf32' or 'tf32x3', not {!r}".format(precision))
+        raise ValueError("precision must be 'auto', 'f64', 'f64_ozaki', 'tf32' or 'tf32x3', not {!r}".format(precision))
     return PRECISIONS[precision]
+
+
+def resolve_precision(precision, N, D, weights=None):
+    """The engine 'auto' stands for at this shape ('f64_ozaki' | 'f64'); any other value is returned as is."""
+    _split(precision)
+    if precision != 'auto':
+        return precision
+    if D < AUTO_OZAKI_MIN_DIM or float(N) * D * D < AUTO_OZAKI_MIN_WORK:
+        return 'f64'
+    if weights is not None and bool((weights < 0).any()):
+        return 'f64'
+    return 'f64_ozaki'
 
 
 def syrk_weighted(X, s=None, l2=0.0, out=None, precision='f64'):
@@ -211,6 +229,7 @@ def syrk_weighted(X, s=None, l2=0.0, out=None, precision='f64'):
     lib = _cabi.require_cuda()
     _mat(X, 'X')
     N, D = X.shape
+    precision = resolve_precision(precision, N, D, s)
     split = _split(precision)
     if s is None and not split:
         s = torch.ones(N, dtype=torch.float64, device=X.device)
@@ -352,13 +371,15 @@ def potrf(H, overwrite=False, check_pd=True):
 # ------------------------------------------------------------- IJ apply ----
 def ij_apply(Hinv, X, resid, out=None, precision='f64'):
     """S (D, N) = -Hinv @ (resid[:, None] * X).T without materialising the
-    cross-Hessian.  ``precision``: 'f64' (DMMA engine, the default) or the
-    optional 'tf32' / 'tf32x3' tcgen05 path."""
+    cross-Hessian.  ``precision``: 'f64' (DMMA engine), 'f64_ozaki' (FP64-grade on the
+    INT8 tensor cores), 'auto' (one of those two by size) or the optional
+    reduced-precision 'tf32' / 'tf32x3' tcgen05 path."""
     lib = _cabi.require_cuda()
     _mat(Hinv, 'Hinv'); _mat(X, 'X')
     N, D = X.shape
     if out is None:
         out = torch.empty((D, N), dtype=torch.float64, device=X.device)
+    precision = resolve_precision(precision, N, D)
     split = _split(precision)
     if precision == 'f64_ozaki':
         ws, wsb = _ws('ij_ozaki', lib.vt_ij_apply_ozaki_workspace_bytes(N, D, OZAKI_SLICES), X.device)

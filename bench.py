@@ -44,13 +44,15 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--n-total', type=int, default=10_000_000)
     ap.add_argument('--dim', type=int, default=1024)
-    ap.add_argument('--cpu-sample', type=int, default=100_000, help='rows of the CPU-baseline sample')
+    ap.add_argument('--cpu-sample', type=int, default=0,
+                    help='rows of the CPU-baseline sample (0: sized from a calibration run, 1e5 .. 1e6 rows)')
     ap.add_argument('--e2e-steps', type=int, default=2)
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--no-tf32', action='store_true', help='skip the rows of the other engines (f64_ozaki, tf32x3, tf32)')
-    ap.add_argument('--precision', default='f64', choices=['f64', 'f64_ozaki', 'tf32x3', 'tf32'],
-                    help="engine of the two contractions for the headline and e2e legs (default: FP64 DMMA)")
+    ap.add_argument('--no-tf32', action='store_true', help='skip the rows of the other engines (f64 DMMA, tf32x3, tf32)')
+    ap.add_argument('--precision', default='auto', choices=['auto', 'f64', 'f64_ozaki', 'tf32x3', 'tf32'],
+                    help="engine of the two contractions for the headline and e2e legs (default 'auto': the library's "
+                         "default, which is the FP64-grade INT8 error-free-slicing engine at this size)")
     ap.add_argument('--engine-rows-only', action='store_true', help=argparse.SUPPRESS)   # child mode, see main()
     ap.add_argument('--engines', action='store_true', help='also measure the other engines when --gpus > 1 '
                     '(by default they are measured on 1 GPU only)')
@@ -80,34 +82,61 @@ def cpu_reference_step(n, d, seed=SEED):
     return t1 - t0
 
 
-def blas_threads():
+def use_all_host_cores():
+    """BLAS threads := all host cores, whatever OMP_NUM_THREADS says (torch.distributed.run exports
+    OMP_NUM_THREADS=1 to its workers, which made the r01 reference arm single-threaded at N > 1).  Returns the
+    number of threads the BLAS pool now uses."""
+    ncores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
     try:
-        from threadpoolctl import threadpool_info
+        from threadpoolctl import threadpool_limits, threadpool_info
+        threadpool_limits(limits=ncores)           # stays in force for the life of the process
         return max([p.get('num_threads', 1) for p in threadpool_info()] + [1])
     except Exception:
-        return os.cpu_count() or 1
+        return 1
+
+
+def cpu_sample_rows(args, cores, steps_total):
+    """Rows of the CPU sample: as many as fit a budget of ~150 s for `steps_total` steps (and host memory),
+    between 1e5 and 1e6, from a 20 000-row calibration step."""
+    if args.cpu_sample > 0:
+        return args.cpu_sample
+    d = args.dim
+    cpu_reference_step(5000, d)                      # BLAS warm-up
+    per_row = cpu_reference_step(20000, d) / 20000.0
+    n = int(150.0 / (steps_total * per_row))
+    try:
+        import psutil
+        n = min(n, int(0.25 * psutil.virtual_memory().available / (4 * 8 * d)))   # X, cross-Hessian, S + slack
+    except Exception:
+        pass
+    return int(max(100_000, min(1_000_000, n)) // 1000 * 1000)
 
 
 def run_reference_arm(args):
+    """--impl reference: the reference's CPU path for this metric on all host cores (oracle port: numpy closed-form
+    assembly + the reference's cho_factor / cho_solve), each step a bounded sample of the workload."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    n, d = args.cpu_sample, args.dim
-    for _ in range(max(args.warmup, 1) if args.warmup < 2 else 1):
-        cpu_reference_step(min(n, 20000), d)
-    times = [cpu_reference_step(n, d) for _ in range(max(1, min(args.steps, 3)))]
-    sec = float(np.median(times))
+    cores = use_all_host_cores()
+    d = args.dim
+    warm = max(1, args.warmup)
+    n = cpu_sample_rows(args, cores, args.steps + warm)
+    for _ in range(warm):
+        cpu_reference_step(n, d)
+    times = [cpu_reference_step(n, d) for _ in range(max(1, args.steps))]
+    sec = float(np.mean(times))
     value = n / sec
-    cores = blas_threads()
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
-        'steps': len(times), 'warmup': 1, 'ms_per_step': sec * 1e3 * (args.n_total / n),
+        'steps': len(times), 'warmup': warm, 'ms_per_step': sec * 1e3 * (args.n_total / n),
         'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': 'logistic IJ N=10M D=1024 f64 (BASELINE configs[1])', 'n_obs': args.n_total,
-                   'dim': d},
+                   'dim': d, 'sample_rows_per_step': n},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                         'sample': '{} of {} observations, D={} (cost is linear in N beyond the D^3/3 factorisation); '
-                                   'numpy closed-form assembly + cho_factor/cho_solve'.format(n, args.n_total, d)},
+                         'sample': '{} of {} observations per step, D={} (cost is linear in N beyond the D^3/3 '
+                                   'factorisation; ms_per_step is scaled to the full N); numpy closed-form assembly + '
+                                   'cho_factor/cho_solve on {} BLAS threads'.format(n, args.n_total, d, cores)},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -235,6 +264,8 @@ def main():
         return sens
 
     peak_tflops = ops.fp64_peak_probe(0.25)
+    engine = ops.resolve_precision(args.precision, n_loc, D, w)        # what 'auto' means at this shard size
+    i8_peak = ops.i8_peak_probe(1.0, 256) if engine == 'f64_ozaki' else None   # sustained: a 1 s bare-MMA loop
 
     # ---- timed region: device-resident inputs --------------------------------
     for _ in range(args.warmup):
@@ -273,14 +304,19 @@ def main():
         return a.elapsed_time(b) / reps, out
     reps = max(2, min(args.steps, 3))
     t_stats, st = timed(lambda: obj.vt_stats(theta, w), reps)
-    t_syrk, H = timed(lambda: ops.syrk_weighted(X, st['s']), reps)
+    t_syrk, H = timed(lambda: ops.syrk_weighted(X, st['s'], precision=engine), reps)
     if world > 1:
         dist.all_reduce(H)
     t_chol, hinv = timed(lambda: ops.potrf(H).inverse(), reps)
-    t_apply, S = timed(lambda: ops.ij_apply(hinv, X, st['resid']), reps)
+    t_apply, S = timed(lambda: ops.ij_apply(hinv, X, st['resid'], precision=engine), reps)
     apply_tflops = 2.0 * D * D * n_loc / (t_apply * 1e-3) / 1e12
     syrk_tflops = float(D) * (D + 1) * n_loc / (t_syrk * 1e-3) / 1e12
     stats_gbs = 8.0 * D * n_loc / (t_stats * 1e-3) / 1e9
+    # conditioning of the Hessian at the optimum (reported: the fused path multiplies by an explicit inverse
+    # only while kappa eps stays far below the parity tolerance - sensitivity_lib.EXPLICIT_INVERSE_MAX_COND)
+    ev = torch.linalg.eigvalsh(H)
+    kappa = float(ev[-1] / ev[0])
+    del ev
 
     # size-independent correctness properties at full size (sampled columns)
     idx = torch.randint(0, n_loc, (256,), device=dev, generator=torch.Generator(device=dev).manual_seed(1))
@@ -300,7 +336,7 @@ def main():
     if args.engine_rows_only or (want_rows and world > 1):
         import gc
         engine_rows = {}
-        for prec in ('f64_ozaki', 'tf32x3', 'tf32'):
+        for prec in (('f64',) if engine == 'f64_ozaki' else ('f64_ozaki',)) + ('tf32x3', 'tf32'):
             try:
                 engine_rows[prec] = engine_row(prec, vt, ops, torch, dist, world, group, dev, X, y, theta, w, st, hinv,
                                                idx, S_cols64, N, D, n_loc, reps, timed)
@@ -346,10 +382,10 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n_s = args.cpu_sample
-        cpu_reference_step(min(n_s, 20000), D)
+        cores = use_all_host_cores()
+        n_s = args.cpu_sample if args.cpu_sample > 0 else cpu_sample_rows(args, cores, 8)    # ~20 s of CPU work
         sec = cpu_reference_step(n_s, D)
-        cpu_baseline = {'value': n_s / sec, 'unit': UNIT, 'cores': blas_threads(), 'kind': 'port',
+        cpu_baseline = {'value': n_s / sec, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                         'sample': '{} of {} observations, D={}; numpy closed-form assembly + '
                                   'cho_factor/cho_solve (oracle port of the reference path)'.format(n_s, N, D)}
 
@@ -364,7 +400,8 @@ def main():
         gc.collect()
         torch.cuda.empty_cache()
         cmd = [sys.executable, os.path.abspath(__file__), '--engine-rows-only', '--n-total', str(N), '--dim', str(D),
-               '--steps', str(min(args.steps, 3)), '--warmup', '1', '--no-e2e', '--no-cpu-baseline']
+               '--steps', str(min(args.steps, 3)), '--warmup', '1', '--no-e2e', '--no-cpu-baseline',
+               '--precision', args.precision]
         try:
             child = subprocess.run(cmd, capture_output=True, text=True, timeout=1500)
             lines = [ln for ln in child.stdout.splitlines() if ln.startswith('{')]
@@ -374,35 +411,61 @@ def main():
             engine_rows = {'error': repr(exc)[:300]}
 
     if rank == 0:
+        S_ = ops.OZAKI_SLICES
+        nprod = S_ * (S_ + 1) // 2
+        if engine == 'f64_ozaki':
+            apply_tops = 2.0 * D * D * n_loc * nprod / (t_apply * 1e-3) / 1e12
+            roofline = {
+                'bound': 'tensor', 'kernel': 'ogemm_kernel<{}> + in-kernel slicing (vt_ij_apply_ozaki: S = -Hinv G^T on '
+                                             'tcgen05.mma.kind::i8)'.format(S_),
+                'achieved': apply_tops, 'peak': i8_peak['tops'], 'unit': 'TFLOP/s', 'frac': apply_tops / i8_peak['tops'],
+                'unit_note': 'INT8 tera-operations per second (multiply + add = 2 ops), reported under the contract\'s '
+                             'TFLOP/s key',
+                'peak_source': 'bare tcgen05.mma.kind::i8 128x256x32 issue loop measured in this run for 1 s '
+                               '(vt_i8_peak_probe: {:.0f} TOP/s, {:.1f} SM clocks per instruction; power-capped '
+                               'clocks - the nominal 4500 TOP/s needs 1.86 GHz); MEASURED_PEAKS.json has no INT8 '
+                               'entry'.format(i8_peak['tops'], i8_peak['clocks_per_mma']),
+                'algorithmic': '{} exact digit products x 2*D^2 INT8 ops per observation ({} balanced base-256 slices '
+                               'per operand); whole vt_ij_apply_ozaki call incl. slicing'.format(nprod, S_),
+                'fp64_equivalent': {'achieved_tflops': apply_tflops, 'fp64_dmma_peak_tflops': peak_tflops,
+                                    'ratio_to_fp64_pipe_peak': apply_tflops / peak_tflops,
+                                    'algorithmic': '2*D^2 flop per observation'},
+                'traffic': None,
+            }
+        else:
+            roofline = {'bound': 'tensor', 'kernel': 'dgemm_kernel<KC,KC> (vt_ij_apply: S = -Hinv G^T)',
+                        'achieved': apply_tflops, 'peak': peak_tflops, 'unit': 'TFLOP/s',
+                        'frac': apply_tflops / peak_tflops,
+                        'peak_source': 'FP64 DMMA probe measured in this run (vt_fp64_peak_probe); '
+                                       'MEASURED_PEAKS.json has no FP64 entry; tools/fp64_peak.cu gave '
+                                       '{} TFLOP/s'.format(FP64_PEAK_FALLBACK_TFLOPS),
+                        'traffic': traffic,
+                        'traffic_source': 'profiles/ncu_traffic.json: dram__bytes_read+write of one ncu --set full '
+                                          'launch at N=1e6, scaled per observation; algorithmic = 16*D bytes/obs',
+                        'algorithmic': '2*D^2 flop per observation'}
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong',
-            'vs_baseline': None, 'dtype': {'f64': 'f64', 'f64_ozaki': 'i8 digit slices -> f64 (error-free slicing)',
-                                           'tf32x3': 'tf32x3', 'tf32': 'tf32'}[args.precision], 'data': 'synthetic',
+            'vs_baseline': None,
+            'dtype': {'f64': 'f64', 'f64_ozaki': 'f64 (contractions: exact i8 digit products -> f64, error-free slicing)',
+                      'tf32x3': 'tf32x3', 'tf32': 'tf32'}[engine], 'data': 'synthetic',
             'config': {'workload': 'logistic IJ N=10M D=1024 f64 (BASELINE configs[1])', 'n_obs': N, 'dim': D,
-                       'precision': args.precision,
+                       'precision': args.precision, 'engine': engine,
                        'sharding': 'observations over {} rank(s), one all-reduce of the DxD Hessian'.format(world),
                        'l2': 'inputs ({:.1f} GB per rank) exceed the 126 MB L2'.format(8.0 * n_loc * D / 1e9),
-                       'grad_norm_at_opt': grad_norm, 'sampled_residual_rel': rel_resid},
+                       'grad_norm_at_opt': grad_norm, 'sampled_residual_rel': rel_resid,
+                       'hessian_condition_number': kappa},
             'clocks': clocks,
             'gpu_launches': launches,
-            'roofline': {'bound': 'tensor', 'kernel': 'dgemm_kernel<KC,KC> (vt_ij_apply: S = -Hinv G^T)',
-                         'achieved': apply_tflops, 'peak': peak_tflops, 'unit': 'TFLOP/s',
-                         'frac': apply_tflops / peak_tflops,
-                         'peak_source': 'FP64 DMMA probe measured in this run (vt_fp64_peak_probe); '
-                                        'MEASURED_PEAKS.json has no FP64 entry; tools/fp64_peak.cu gave '
-                                        '{} TFLOP/s'.format(FP64_PEAK_FALLBACK_TFLOPS),
-                         'traffic': traffic,
-                         'traffic_source': 'profiles/ncu_traffic.json: dram__bytes_read+write of one ncu --set full '
-                                           'launch at N=1e6, scaled per observation; algorithmic = 16*D bytes/obs',
-                         'algorithmic': '2*D^2 flop per observation'},
+            'roofline': roofline,
             'kernels': {
-                'ij_apply': {'ms': t_apply, 'tflops': apply_tflops, 'frac_fp64_peak': apply_tflops / peak_tflops},
-                'syrk_weighted': {'ms': t_syrk, 'tflops_algorithmic_D(D+1)': syrk_tflops,
-                                  'frac_fp64_peak': syrk_tflops / peak_tflops},
+                'ij_apply': {'ms': t_apply, 'fp64_equiv_tflops': apply_tflops, 'ratio_to_fp64_pipe_peak': apply_tflops / peak_tflops},
+                'syrk_weighted': {'ms': t_syrk, 'fp64_equiv_tflops_algorithmic_D(D+1)': syrk_tflops,
+                                  'ratio_to_fp64_pipe_peak': syrk_tflops / peak_tflops},
                 'glm_stats': {'ms': t_stats, 'gb_per_s': stats_gbs,
                               'frac_hbm_peak': stats_gbs / peaks['hbm_gbs'] if 'hbm_gbs' in peaks else None},
                 'potrf_plus_inverse': {'ms': t_chol},
+                'fp64_dmma_peak_tflops': peak_tflops, 'int8_peak': i8_peak,
             },
             'cpu_baseline': cpu_baseline,
             'e2e': e2e,
@@ -415,13 +478,14 @@ def main():
 
 
 ENGINE_NOTES = {
-    'f64_ozaki': ('both contractions on tcgen05.mma.kind::i8: 8 error-free 7-bit slices per operand (56 bits), 36 exact INT8 '
-                  'products, INT32 accumulators in TMEM, INT64/FP64 recombination; statistics, Cholesky and inverse in '
-                  'FP64; held to the same rtol 1e-8 bar as the default path'),
+    'f64': 'both contractions on the FP64 DMMA engine (mma.sync m8n8k4, cp.async ring) - the r01 default',
+    'f64_ozaki': ('both contractions on tcgen05.mma.kind::i8: 7 balanced base-256 slices per operand (54 bits), 28 exact '
+                  'INT8 products, INT32 accumulators in TMEM, FP64 recombination; statistics, Cholesky and inverse in '
+                  'FP64; held to the same rtol 1e-8 bar as the FP64 DMMA path'),
     'tf32x3': 'both contractions on tcgen05.mma.kind::tf32 with a three-term hi/lo split; the rest in FP64',
     'tf32': 'both contractions on tcgen05.mma.kind::tf32 (TMEM accumulators, TMA operands); the rest in FP64',
 }
-ENGINE_TOL = {'f64_ozaki': 1e-8, 'tf32x3': 2e-4, 'tf32': 5e-3}
+ENGINE_TOL = {'f64': 1e-8, 'f64_ozaki': 1e-8, 'tf32x3': 2e-4, 'tf32': 5e-3}
 
 
 def engine_row(prec, vt, ops, torch, dist, world, group, dev, X, y, theta, w, st, hinv, idx, S_cols64, N, D, n_loc, reps,
@@ -443,21 +507,12 @@ def engine_row(prec, vt, ops, torch, dist, world, group, dev, X, y, theta, w, st
     bar = float(torch.max(diff / (1e-8 * torch.abs(S_cols64) + 1e-12 * smax)))
     t_ap, _ = timed(lambda: ops.ij_apply(hinv, X, st['resid'], out=S32, precision=prec), reps)
     row = {'value': N / (t_step * 1e-3), 'unit': UNIT, 'ms_per_step': t_step,
-           'sampled_sens_err_vs_f64_dmma': {'normwise': err_norm, 'worst_ratio_to_rtol1e-8_bar': bar},
-           'tolerance': ('rtol 1e-8 elementwise + 1e-12 max|ref| floor (the FP64 parity bar)' if prec == 'f64_ozaki'
+           'sampled_sens_err_vs_headline_engine': {'normwise': err_norm, 'worst_ratio_to_rtol1e-8_bar': bar},
+           'tolerance': ('rtol 1e-8 elementwise + 1e-12 max|ref| floor (the FP64 parity bar)' if prec in ('f64', 'f64_ozaki')
                          else '{:g} normwise'.format(ENGINE_TOL[prec])),
-           'within_tolerance': bool(bar <= 1.0) if prec == 'f64_ozaki' else bool(err_norm <= ENGINE_TOL[prec]),
+           'within_tolerance': bool(bar <= 1.0) if prec in ('f64', 'f64_ozaki') else bool(err_norm <= ENGINE_TOL[prec]),
            'ij_apply_ms': t_ap, 'ij_apply_fp64_equiv_tflops': 2.0 * D * D * n_loc / (t_ap * 1e-3) / 1e12,
            'engine': ENGINE_NOTES[prec]}
-    if prec == 'f64_ozaki':
-        S_ = ops.OZAKI_SLICES
-        tops = 2.0 * D * D * n_loc * (S_ * (S_ + 1) // 2) / (t_ap * 1e-3) / 1e12
-        row['ij_apply_roofline'] = {'bound': 'tensor (INT8)', 'achieved': tops, 'peak': 4500.0, 'unit': 'TOP/s',
-                                    'frac': tops / 4500.0,
-                                    'peak_source': 'nominal dense INT8 peak of B200 (MEASURED_PEAKS.json has no INT8 entry)',
-                                    'algorithmic': '{} digit products of 2*D^2 INT8 ops per observation ({} slices); '
-                                                   'ncu: sm__pipe_tc_cycles_active 90 % (profiles/ncu_full_r01d_kernels.csv)'
-                                                   .format(S_ * (S_ + 1) // 2, S_)}
     t_sy, _h = timed(lambda: ops.syrk_weighted(X, st['s'], precision=prec), reps)
     row.update({'syrk_ms': t_sy, 'syrk_fp64_equiv_tflops_algorithmic': float(D) * (D + 1) * n_loc / (t_sy * 1e-3) / 1e12})
     return row

@@ -213,6 +213,8 @@ int vt_cg_update_xr(int D, const double* p, const double* q, double* x, double* 
  * pointer may be NULL.                                                       */
 int vt_block_potrf_batched(double* blocks, int64_t G, int M, int32_t* info, void* stream);
 int vt_block_trsm_batched(const double* Lb, double* C, int64_t G, int M, int Dg, void* stream);
+/* C_g <- L_g^{-T} C_g in place: the backward half of a multi-right-hand-side block solve (C: G x M x K). */
+int vt_block_trsmt_batched(const double* Lb, double* C, int64_t G, int M, int Dg, void* stream);
 int vt_block_solve_batched(const double* Lb, double* b, int64_t G, int M, int mode, void* stream);
 int vt_tall_gemv(const double* Z, int64_t R, int Dg, const double* x, double alpha, double* y, double beta,
                  void* stream);

@@ -205,3 +205,74 @@ def test_streamed_host_input_matches_resident(vt):
     assert_close(sens_s.get_dopt_dhyper(), sens_r.get_dopt_dhyper(), rtol=1e-9, atol_scale=1e-13)
     cf = models.glm_closed_form(X, y, theta, w, l2=0.2)
     assert_close(sens_s.get_dopt_dhyper(), -np.linalg.solve(cf['hessian'], cf['cross_hessian']))
+
+
+@pytest.mark.parametrize('kappa', [1e2, 1e6, 1e9])
+def test_conditioning_sweep(vt, kappa):
+    """Forward error of the IJ sensitivities against an extended-precision oracle (oracle/highprec.py) as the Hessian
+    becomes ill conditioned.  The reference substitutes with the Cholesky factor (``solver_lib.py:29``); the fused
+    path multiplies by an explicit inverse only while a lower bound on kappa(H) keeps kappa eps far below the parity
+    tolerance and substitutes otherwise - at every kappa its error must be comparable to the error scipy's
+    ``cho_solve`` (the reference's own algorithm, float64) makes on the same inputs."""
+    import scipy.linalg
+    from oracle import models, highprec
+    n, d = 3000, 40
+    X, y, _ = models.synth_logistic(41, n, d)
+    X = X * np.sqrt(d) * np.logspace(0, -0.5 * np.log10(kappa), d)[None, :]       # column scales: kappa(H) ~ kappa
+    w = np.ones(n)
+    theta = models.glm_newton(X, y, w, iters=100)
+    H_ld, S_ld = highprec.logistic_ij_ld(X, y, theta, w)
+    S_ref = np.asarray(S_ld, dtype=np.float64)
+    true_kappa = np.linalg.cond(np.asarray(H_ld, dtype=np.float64))
+    assert 0.05 * kappa < true_kappa < 200 * kappa
+    cf = models.glm_closed_form(X, y, theta, w)
+    S_scipy = -scipy.linalg.cho_solve(scipy.linalg.cho_factor(cf['hessian']), cf['cross_hessian'])
+
+    def err(S):      # row-wise: the rows of S live on very different scales here
+        return float(np.max(np.max(np.abs(np.asarray(S) - S_ref), axis=1) / np.max(np.abs(S_ref), axis=1)))
+    e_scipy = err(S_scipy)
+    obj = vt.objectives.GLMObjective(X, y, family='logistic')
+    sens = vt.HyperparameterSensitivityLinearApproximation(obj, theta, w)
+    e_ours = err(sens.get_dopt_dhyper())
+    assert sens.hessian_cond_lower_bound <= 1.01 * true_kappa
+    assert sens.used_explicit_inverse == (sens.hessian_cond_lower_bound <= 1e6)
+    if kappa >= 1e9:
+        assert not sens.used_explicit_inverse               # substitution, like the reference
+    if kappa <= 1e2:
+        assert sens.used_explicit_inverse
+    floor = 50 * np.finfo(np.float64).eps
+    assert e_ours <= 10 * max(e_scipy, floor), (kappa, e_ours, e_scipy)
+    # the parity bar itself holds whenever kappa eps allows it at all
+    if kappa <= 1e6:
+        assert_close(sens.get_dopt_dhyper(), S_scipy, rtol=1e-8, atol_scale=1e-9, what='kappa {:g}'.format(kappa))
+
+
+def test_default_engine_at_bench_width_vs_oracle(vt):
+    """The DEFAULT path (precision='auto') at the width of BASELINE config 2 (D = 1024) and N = 2e5 observations:
+    'auto' resolves to the INT8 error-free-slicing engine here, and the whole (D, N) result meets the rtol 1e-8
+    parity bar against the oracle's closed form + the reference's cho_factor / cho_solve."""
+    from oracle import models, solver_lib as osl
+    n, d = 200_000, 1024
+    assert vt.ops.resolve_precision('auto', n, d) == 'f64_ozaki'
+    assert vt.ops.resolve_precision('auto', 1000, 10) == 'f64'
+    X, y, _ = models.synth_logistic(20261017, n, d)
+    w = np.ones(n)
+    Xd, yd, wd = _dev(X), _dev(y), _dev(w)
+    obj = vt.objectives.GLMObjective(Xd, yd, family='logistic')
+    assert obj.precision == 'auto'
+    theta = torch.zeros(d, dtype=torch.float64, device='cuda')
+    for _ in range(30):                                     # Newton on the same kernels
+        st = obj.vt_stats(theta, wd)
+        step = vt.ops.potrf(obj.vt_hessian(theta, wd, st)).solve(st['grad'])
+        theta = theta - step
+        if float(torch.linalg.vector_norm(step)) < 1e-12:
+            break
+    sens = vt.HyperparameterSensitivityLinearApproximation(obj, theta, wd, validate_optimum=True, grad_tol=1e-8)
+    cf = models.glm_closed_form(X, y, theta.cpu().numpy(), w)
+    S_ref = -1 * osl.get_cholesky_solver(cf['hessian'])(cf['cross_hessian'])
+    assert_close(sens.get_hessian_at_opt(), cf['hessian'], rtol=1e-9, what='H (auto engine)')
+    assert_close(sens.get_dopt_dhyper(), S_ref, rtol=1e-8, atol_scale=1e-12, what='dopt_dhyper (auto engine, D=1024)')
+    # the explicit DMMA engine on the same inputs
+    obj64 = vt.objectives.GLMObjective(Xd, yd, family='logistic', precision='f64')
+    sens64 = vt.HyperparameterSensitivityLinearApproximation(obj64, theta, wd)
+    assert_close(sens64.get_dopt_dhyper(), S_ref, rtol=1e-8, atol_scale=1e-12, what='dopt_dhyper (f64 DMMA, D=1024)')

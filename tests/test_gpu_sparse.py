@@ -202,6 +202,8 @@ def test_block_kernels_directly(vt):
         assert_close(y, np.stack([np.linalg.solve(Lnp[g], b[g]) for g in range(G)]), rtol=1e-9, atol_scale=1e-12)
         yt = vt.ops.block_solve(Lb, _dev(b), transpose=True)
         assert_close(yt, np.stack([np.linalg.solve(Lnp[g].T, b[g]) for g in range(G)]), rtol=1e-9, atol_scale=1e-12)
+        Zt = vt.ops.block_trsm(Lb, _dev(C), transpose=True)
+        assert_close(Zt, np.stack([np.linalg.solve(Lnp[g].T, C[g]) for g in range(G)]), rtol=1e-9, atol_scale=1e-12)
         Z2 = Z.reshape(G * M, Dg)
         xg = rng.normal(size=Dg)
         u = rng.normal(size=G * M)
@@ -211,3 +213,51 @@ def test_block_kernels_directly(vt):
     bad[2, 1, 1] = -1.0
     with pytest.raises(np.linalg.LinAlgError):
         vt.ops.block_potrf(_dev(bad))
+
+
+@pytest.mark.parametrize('K', [1, 2, 3, 40, 130])
+def test_block_arrow_solver_many_right_hand_sides(vt, K):
+    """(d, K) right-hand sides are solved together (SURVEY 8f-2 / the matrix-RHS call sites
+    ``sensitivity_lib.py:226``, ``lr_cov_lib.py:172``): one or two columns through the matrix-vector kernels, more
+    through the GEMM engine with Z read twice per solve - every K against a dense solve, shape preserved."""
+    from vittles_b200.sparse_hessian_lib import BlockArrowHessian
+    rng = np.random.RandomState(100 + K)
+    G, M, Dg = 257, 19, 96
+    d = G * M + Dg
+    perm = rng.permutation(d)
+    sa, gi = perm[:G * M].reshape(G, M), perm[G * M:]
+    a = rng.normal(size=(G, M, M))
+    blocks = a @ a.transpose(0, 2, 1) / M + np.eye(M)
+    cross = 0.02 * rng.normal(size=(G, M, Dg))
+    g0 = rng.normal(size=(Dg, Dg))
+    hgg = g0 @ g0.T / Dg + 3.0 * np.eye(Dg)
+    h = BlockArrowHessian(d, torch.as_tensor(sa, device='cuda'), torch.as_tensor(gi, device='cuda'),
+                          blocks=_dev(blocks), cross=_dev(cross), hgg=_dev(hgg))
+    dense = h.todense()
+    B = rng.normal(size=(d, K))
+    solve = vt.solver_lib.get_cholesky_solver(h)
+    out = solve(B)
+    assert out.shape == (d, K)
+    assert_close(out, np.linalg.solve(dense, B), rtol=1e-8, atol_scale=1e-11, what='K = {}'.format(K))
+    # H @ v without densifying, and the device-side dense form
+    assert_close(h @ B, dense @ B, rtol=1e-11, atol_scale=1e-13)
+    assert_close(h.to_dense_tensor(), dense, rtol=0, atol_scale=1e-15)
+
+
+def test_blocks_wider_than_the_batched_kernels_fall_back_to_the_dense_solver(vt):
+    """The batched kernels hold one block per warp / CTA (M <= 32); the reference's SuperLU path takes any block
+    size (``solver_lib.py:46-48``), so wider blocks go through the dense GPU Cholesky instead of failing."""
+    from vittles_b200.sparse_hessian_lib import BlockArrowHessian
+    rng = np.random.RandomState(5)
+    G, M, Dg = 6, 40, 9
+    d = G * M + Dg
+    a = rng.normal(size=(G, M, M))
+    blocks = a @ a.transpose(0, 2, 1) / M + np.eye(M)
+    cross = 0.05 * rng.normal(size=(G, M, Dg))
+    hgg = 4.0 * np.eye(Dg)
+    sa = np.arange(G * M).reshape(G, M)
+    gi = G * M + np.arange(Dg)
+    h = BlockArrowHessian(d, torch.as_tensor(sa, device='cuda'), torch.as_tensor(gi, device='cuda'),
+                          blocks=_dev(blocks), cross=_dev(cross), hgg=_dev(hgg))
+    B = rng.normal(size=(d, 3))
+    assert_close(vt.solver_lib.get_cholesky_solver(h)(B), np.linalg.solve(h.todense(), B), rtol=1e-8, atol_scale=1e-11)

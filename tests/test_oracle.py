@@ -221,3 +221,21 @@ def test_int8_slicing_model_extreme_digits():
     x = -2.0 * sum(2.0 ** (-8 * s) for s in range(S))                 # 2^-6 sum_s (-128) 2^-8s
     dropped = sum((2 * S - 1 - l) * 2.0 ** (2 - 8 * l) for l in range(S, 2 * S - 1))
     np.testing.assert_allclose(out, K * (x * x - dropped), rtol=1e-15)
+
+
+def test_extended_precision_oracle_agrees_with_scipy_when_well_conditioned():
+    """oracle/highprec.py (longdouble Cholesky solve) against the reference's cho_factor / cho_solve on a
+    well-conditioned logistic problem: they agree to float64 rounding, and the longdouble residual is ~1e-19."""
+    import scipy.linalg
+    from oracle import models, highprec
+    n, d = 400, 12
+    X, y, _ = models.synth_logistic(3, n, d)
+    w = np.ones(n)
+    theta = models.glm_newton(X, y, w)
+    H_ld, S_ld = highprec.logistic_ij_ld(X, y, theta, w)
+    cf = models.glm_closed_form(X, y, theta, w)
+    S = -scipy.linalg.cho_solve(scipy.linalg.cho_factor(cf['hessian']), cf['cross_hessian'])
+    np.testing.assert_allclose(np.asarray(S_ld, dtype=np.float64), S, rtol=1e-10, atol=1e-13 * np.abs(S).max())
+    G_ld = ((1 / (1 + np.exp(-(X.astype(np.longdouble) @ theta.astype(np.longdouble)))) - y)[:, None] * X).T
+    resid = np.abs(H_ld @ S_ld + G_ld).max() / np.abs(G_ld).max()
+    assert float(resid) < 1e-17

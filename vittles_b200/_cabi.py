@@ -62,6 +62,7 @@ SIGNATURES = {
     'vt_cg_update_xr': (_I, [_I, _P, _P, _P, _P, _P, _P]),
     'vt_block_potrf_batched': (_I, [_P, _I64, _I, _P, _P]),
     'vt_block_trsm_batched': (_I, [_P, _P, _I64, _I, _I, _P]),
+    'vt_block_trsmt_batched': (_I, [_P, _P, _I64, _I, _I, _P]),
     'vt_block_solve_batched': (_I, [_P, _P, _I64, _I, _I, _P]),
     'vt_tall_gemv': (_I, [_P, _I64, _I, _P, _D, _P, _D, _P]),
     'vt_tall_colsum_workspace_bytes': (_SZ, [_I]),

@@ -294,7 +294,10 @@ int vt_block_potrf_batched(double* blocks, int64_t G, int M, int32_t* info, void
   return block_potrf(blocks, G, M, info, S(stream));
 }
 int vt_block_trsm_batched(const double* Lb, double* C, int64_t G, int M, int Dg, void* stream) {
-  return block_trsm(Lb, C, G, M, Dg, S(stream));
+  return block_trsm(Lb, C, G, M, Dg, 0, S(stream));
+}
+int vt_block_trsmt_batched(const double* Lb, double* C, int64_t G, int M, int Dg, void* stream) {
+  return block_trsm(Lb, C, G, M, Dg, 1, S(stream));
 }
 int vt_block_solve_batched(const double* Lb, double* b, int64_t G, int M, int mode, void* stream) {
   return block_solve(Lb, b, G, M, mode, S(stream));

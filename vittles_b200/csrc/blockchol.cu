@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(128) block_potrf_kernel(double* blocks, long G
 // thread has all M loads of its column in flight before the substitution
 // starts (HBM bound: 16 M Dg bytes per block).
 constexpr int TRSM_BPC = 4;
-template <int MT>
+template <int MT, bool TR>
 __global__ void __launch_bounds__(256) block_trsm_kernel(const double* __restrict__ Lb, double* __restrict__ C, long G,
                                                          int M, int Dg) {
   __shared__ double sl[TRSM_BPC][MT * MT];
@@ -101,13 +101,26 @@ __global__ void __launch_bounds__(256) block_trsm_kernel(const double* __restric
 #pragma unroll
       for (int i = 0; i < MT; ++i)
         if (i < M) z[i] = Cg[(long)i * Dg];
+      if constexpr (!TR) {
 #pragma unroll
-      for (int i = 0; i < MT; ++i) {
-        if (i < M) {
-          double s = z[i];
+        for (int i = 0; i < MT; ++i) {
+          if (i < M) {
+            double s = z[i];
 #pragma unroll
-          for (int k = 0; k < i; ++k) s = fma(-L[i * M + k], z[k], s);
-          z[i] = s * sinv[b][i];
+            for (int k = 0; k < i; ++k) s = fma(-L[i * M + k], z[k], s);
+            z[i] = s * sinv[b][i];
+          }
+        }
+      } else {                                   // L^T z' = z: backward substitution down the columns of L
+#pragma unroll
+        for (int i = MT - 1; i >= 0; --i) {
+          if (i < M) {
+            double s = z[i];
+#pragma unroll
+            for (int k = i + 1; k < MT; ++k)
+              if (k < M) s = fma(-L[k * M + i], z[k], s);
+            z[i] = s * sinv[b][i];
+          }
         }
       }
 #pragma unroll
@@ -283,13 +296,19 @@ int block_potrf(double* blocks, long G, int M, int* info, cudaStream_t stream) {
   return VT_OK;
 }
 
-int block_trsm(const double* Lb, double* C, long G, int M, int Dg, cudaStream_t stream) {
+int block_trsm(const double* Lb, double* C, long G, int M, int Dg, int transpose, cudaStream_t stream) {
   VT_REQUIRE(Lb && C && G >= 1 && M >= 1 && M <= MAXM && Dg >= 1, "block_trsm: bad arguments");
   const int grid = grid_for(G, TRSM_BPC, 3);
-  if (M <= 8) block_trsm_kernel<8><<<grid, 256, 0, stream>>>(Lb, C, G, M, Dg);
-  else if (M <= 16) block_trsm_kernel<16><<<grid, 256, 0, stream>>>(Lb, C, G, M, Dg);
-  else if (M <= 24) block_trsm_kernel<24><<<grid, 256, 0, stream>>>(Lb, C, G, M, Dg);
-  else block_trsm_kernel<32><<<grid, 256, 0, stream>>>(Lb, C, G, M, Dg);
+#define VT_TRSM(MT)                                                                      \
+  do {                                                                                   \
+    if (transpose) block_trsm_kernel<MT, true><<<grid, 256, 0, stream>>>(Lb, C, G, M, Dg);  \
+    else block_trsm_kernel<MT, false><<<grid, 256, 0, stream>>>(Lb, C, G, M, Dg);           \
+  } while (0)
+  if (M <= 8) VT_TRSM(8);
+  else if (M <= 16) VT_TRSM(16);
+  else if (M <= 24) VT_TRSM(24);
+  else VT_TRSM(32);
+#undef VT_TRSM
   VT_LAUNCH_CHECK();
   return VT_OK;
 }

@@ -10,7 +10,7 @@ constexpr int BLOCK_MAXM = 32;
 // *info (device int): 0, or 1 + index of a block with a non-positive pivot.
 int block_potrf(double* blocks, long G, int M, int* info, cudaStream_t stream);
 // C_g <- L_g^{-1} C_g for G blocks of shape (M, Dg).
-int block_trsm(const double* Lb, double* C, long G, int M, int Dg, cudaStream_t stream);
+int block_trsm(const double* Lb, double* C, long G, int M, int Dg, int transpose, cudaStream_t stream);
 // b_g <- L_g^{-1} b_g (mode 0) or L_g^{-T} b_g (mode 1), b of shape (G, M).
 int block_solve(const double* Lb, double* b, long G, int M, int mode, cudaStream_t stream);
 // y = beta * y + alpha * Z x  for a row-major Z (R x Dg) with R very long.

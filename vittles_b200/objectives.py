@@ -203,6 +203,17 @@ class GLMObjective(StructuredObjective):
         self._wait_resident()
         return ops.ij_apply(hinv, self.X, stats['resid'], out=out, precision=self.precision)
 
+    def vt_ij_sensitivity_by_substitution(self, factor, stats, out=None):
+        """The same (D, N_local) matrix by forward / backward substitution with the Cholesky factor - what the
+        reference's ``cho_solve`` does (``solver_lib.py:29``): -G^T is formed once (the transposing GEMM engine
+        against the identity, the residuals as the column scale) and solved in place.  Three GEMM-sized passes
+        instead of one, backward stable whatever the conditioning of H."""
+        self._wait_resident()
+        n, d = self.X.shape
+        eye = torch.eye(d, dtype=torch.float64, device=self.X.device)
+        gt = ops.gemm(eye, self.X, 'KC', 'KC', alpha=-1.0, colscale=stats['resid'], out=out)
+        return factor.solve(gt, overwrite=True)
+
     def vt_hvp_fn(self, theta, w):
         """mat_times_vec for get_cg_solver: v -> H v, one fused pass over X."""
         s = self.vt_stats(theta, w, want_grad=False)['s']
@@ -370,4 +381,5 @@ class GMMVBObjective(StructuredObjective):
         if want_g:
             rsum = self._allreduce(out['r'].sum(0))
             hgg = torch.diag((rsum + self.prior_prec).repeat_interleave(self.d))
-        return BlockArrowHessian(self.dim, sparsity_array, gi, blocks=out['blocks'], cross=out['cross'], hgg=hgg)
+        return BlockArrowHessian(self.dim, sparsity_array, gi, blocks=out['blocks'], cross=out['cross'], hgg=hgg,
+                                 group=self.group)

@@ -85,6 +85,15 @@ def fp64_peak_probe(seconds=0.3):
     return tf.value
 
 
+def i8_peak_probe(seconds=1.0, n_tile=256):
+    """{'tops': dense INT8 TOP/s of a bare tcgen05.mma.kind::i8 loop of 128 x n_tile x 32 instructions run for
+    about `seconds`, 'clocks_per_mma': SM clocks per instruction} - the denominator of the slicing engine's roofline."""
+    lib = _cabi.require_cuda()
+    tops, clk = ctypes.c_double(), ctypes.c_double()
+    check(lib.vt_i8_peak_probe(float(seconds), int(n_tile), ctypes.byref(tops), ctypes.byref(clk), stream()))
+    return {'tops': tops.value, 'clocks_per_mma': clk.value, 'n_tile': int(n_tile), 'seconds': float(seconds)}
+
+
 # ------------------------------------------------------------------ GEMM ----
 def gemm(A, B, amode='KC', bmode='KC', alpha=1.0, beta=0.0, out=None, M=None, N=None, K=None,
          kscale=None, colscale=None, rowscale=None, lower=False, mirror=False, tile=0):
@@ -342,6 +351,12 @@ class CholeskyFactor:
         eye = torch.eye(self.dim, dtype=torch.float64, device=self.L.device)
         return self.solve(eye, overwrite=True)
 
+    def cond_lower_bound(self):
+        """(max_i L_ii / min_i L_ii)^2 <= kappa_2(L L^T): a free lower bound on the condition number of the
+        factorised matrix (one D-element reduction), used to decide whether the explicit inverse is safe."""
+        d = torch.diagonal(self.L)
+        return float((d.max() / d.min()) ** 2)
+
 
 def potrf(H, overwrite=False, check_pd=True):
     """Cholesky-factor a dense symmetric positive-definite matrix on the GPU.
@@ -463,13 +478,14 @@ def block_potrf(blocks, check_pd=True):
     return blocks
 
 
-def block_trsm(Lb, C):
-    """C[g] <- L[g]^{-1} C[g] in place, C of shape (G, M, Dg)."""
+def block_trsm(Lb, C, transpose=False):
+    """C[g] <- L[g]^{-1} C[g] (or L[g]^{-T} C[g]) in place, C of shape (G, M, Dg)."""
     lib = _cabi.require_cuda()
     G, M, Dg = C.shape
     if not C.is_contiguous():
         raise ValueError('C must be contiguous')
-    check(lib.vt_block_trsm_batched(ptr(_f64(Lb, 'Lb')), ptr(_f64(C, 'C')), G, M, Dg, stream()))
+    fn = lib.vt_block_trsmt_batched if transpose else lib.vt_block_trsm_batched
+    check(fn(ptr(_f64(Lb, 'Lb')), ptr(_f64(C, 'C')), G, M, Dg, stream()))
     return C
 
 

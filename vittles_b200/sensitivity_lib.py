@@ -181,6 +181,11 @@ class EstimatingEquationLinearApproximation:
         return get_linear_function(self._input_val0, self._hyper_val0, self._sens_mat)
 
 
+# kappa(H) above which the fused IJ path stops multiplying by an explicit inverse: kappa * 2^-53 ~ 1e-10 leaves two
+# orders of magnitude to the rtol 1e-8 parity bar (tests/test_gpu_ij.py::test_conditioning_sweep)
+EXPLICIT_INVERSE_MAX_COND = 1e6
+
+
 class HyperparameterSensitivityLinearApproximation(EstimatingEquationLinearApproximation):
     """Linear dependence of an optimum on a hyperparameter:
     d theta_hat / d lambda = -H^{-1} d^2 f / d theta d lambda
@@ -262,9 +267,19 @@ class HyperparameterSensitivityLinearApproximation(EstimatingEquationLinearAppro
         factor = getattr(self._hess_solver, 'factor', None)
         if factor is None:
             factor = ops.potrf(to_device(self._hess0, self._input_val0.device))
-        self._hinv = factor.inverse()
         self._estimating_equation_jac0 = None
-        self._sens_mat = self._objective_fun.vt_ij_sensitivity(self._hinv, self._stats)
+        # The fused path multiplies by an explicit H^{-1} (one GEMM); the reference substitutes with the Cholesky
+        # factor (``solver_lib.py:29``).  The two agree to ~kappa(H) eps, so the explicit inverse is used only while
+        # a lower bound on kappa(H) keeps that below the parity tolerance; otherwise substitution, like upstream.
+        self.hessian_cond_lower_bound = factor.cond_lower_bound()
+        self.used_explicit_inverse = self.hessian_cond_lower_bound <= EXPLICIT_INVERSE_MAX_COND or \
+            not hasattr(self._objective_fun, 'vt_ij_sensitivity_by_substitution')
+        if self.used_explicit_inverse:
+            self._hinv = factor.inverse()
+            self._sens_mat = self._objective_fun.vt_ij_sensitivity(self._hinv, self._stats)
+        else:
+            self._hinv = None
+            self._sens_mat = self._objective_fun.vt_ij_sensitivity_by_substitution(factor, self._stats)
 
     def set_base_values(self, opt_par_value, hyper_par_value, hessian_at_opt, cross_hess_at_opt,
                         validate_optimum=True, grad_tol=None):

@@ -81,11 +81,14 @@ class BlockArrowHessian:
     be ``None`` (= zero).  ``sparsity_array`` (G, M) and ``global_inds`` (Dg,)
     place the parts in the flat parameter vector."""
 
-    def __init__(self, d, sparsity_array, global_inds, blocks=None, cross=None, hgg=None):
+    def __init__(self, d, sparsity_array, global_inds, blocks=None, cross=None, hgg=None, group=None):
         self.shape = (d, d)
         self.sparsity_array = sparsity_array      # torch int64 (G, M) on the device
         self.global_inds = global_inds            # torch int64 (Dg,)
         self.blocks, self.cross, self.hgg = blocks, cross, hgg
+        # torch.distributed group over which the blocks are SHARDED (every rank holds the blocks / cross blocks of
+        # its own observations; `hgg` is the complete global block, replicated); None: everything is here
+        self.group = group
 
     @classmethod
     def from_sparse(cls, h, max_block=32, device=None):
@@ -112,7 +115,8 @@ class BlockArrowHessian:
             return b if a is None else (a if b is None else a + b)
         ginds = self.global_inds if self.global_inds.numel() >= other.global_inds.numel() else other.global_inds
         return BlockArrowHessian(self.shape[0], self.sparsity_array, ginds, add(self.blocks, other.blocks),
-                                 add(self.cross, other.cross), add(self.hgg, other.hgg))
+                                 add(self.cross, other.cross), add(self.hgg, other.hgg),
+                                 group=self.group if self.group is not None else other.group)
 
     # -- conversions (small problems / interoperability) ----------------------
     def tocoo(self):
@@ -198,6 +202,9 @@ class BlockArrowHessian:
         if self.sparsity_array.shape[1] > BLOCK_MAXM:
             # the batched kernels keep one block per warp / CTA in shared memory (M <= 32); wider blocks go the way
             # the reference's SuperLU goes - a general factorisation - here the dense GPU Cholesky
+            if self.group is not None:
+                raise ValueError('block-arrow solver: blocks wider than {} are not supported on a sharded Hessian'
+                                 .format(BLOCK_MAXM))
             if self.shape[0] > 32768:
                 raise ValueError('block-arrow solver: blocks of size {} exceed the batched kernels\' limit of {} and '
                                  'the matrix (dimension {}) is too large to densify'.format(

@@ -100,6 +100,11 @@ size_t vt_glm_workspace_bytes(int D);
 int vt_glm_stats(const double* X, int64_t ldx, int64_t N, int D, const double* theta, const double* y,
                  const double* w, int family, double* z, double* resid, double* s, double* grad, double l2,
                  void* workspace, size_t workspace_bytes, void* stream);
+/* q <= 4 Hessian-vector products in ONE pass over X: out (q x D) = V X^T diag(s) X + ridge V, V (q x D)
+ * row-major - the shared mat_times_vec of a multi-right-hand-side CG (D <= 2048 for q > 1). */
+size_t vt_glm_hvp_multi_workspace_bytes(int D, int q);
+int vt_glm_hvp_multi(const double* X, int64_t ldx, int64_t N, int D, const double* s, const double* V, int q,
+                     double ridge, double* out, void* workspace, size_t workspace_bytes, void* stream);
 int vt_glm_hvp(const double* X, int64_t ldx, int64_t N, int D, const double* s, const double* v, double ridge,
                double* out, void* workspace, size_t workspace_bytes, void* stream);
 size_t vt_glm_dirderiv_workspace_bytes(int64_t N, int D);
@@ -190,13 +195,24 @@ size_t vt_gemv_workspace_bytes(int M, int64_t N);
 int vt_gemv(const double* A, int64_t lda, int M, int64_t N, const double* x, double alpha, const double* y0,
             double beta, double* y, void* workspace, size_t workspace_bytes, void* stream);
 
-/* ---- Conjugate-gradient vector kernels --------------------------------------
- * One scipy-cg iteration (solver_lib.py:93) is
- *   vt_cg_update_p  ->  q = mat_times_vec(p)  ->  vt_cg_update_xr.
- * `state` is 8 device doubles: {rho, rho_prev, p.q, |r|^2, |b|^2, ...}.      */
-int vt_cg_init(int D, const double* b, double* x, double* r, double* state, void* stream);
-int vt_cg_update_p(int D, const double* r, double* p, double* state, int first, void* stream);
-int vt_cg_update_xr(int D, const double* p, const double* q, double* x, double* r, double* state, void* stream);
+/* ---- Conjugate-gradient vector kernels, batched over K right-hand sides -------
+ * Replaces scipy.sparse.linalg.cg behind get_cg_solver (solver_lib.py:91-97, legacy
+ * stopping rule |r| < max(atol, rtol |b|)).  Vectors are rows of (K, D) arrays;
+ * `state` is K x 8 device doubles {rho, rho_prev, p.q, |r|^2, |b|^2, tol, status,
+ * matvecs}, status 1 = running, 0 = converged, 2 = stopped at maxiter.  One
+ * iteration of all K columns is
+ *   vt_cg_batch_update_p  ->  Q = mat_times_vec(P)  ->  vt_cg_batch_update_xr;
+ * every column follows scipy's iteration on its own scalars and freezes (P row =
+ * 0) once it has converged; the host reads `state` only to learn that all have.
+ * update_p: Z (K x D, may be NULL) = preconditioned residuals M r computed by the
+ * caller, else minv (D, may be NULL) = the diagonal of a Jacobi preconditioner.
+ * keep_xr != 0 in init: X and R already hold x0 and b - A x0.                     */
+int vt_cg_batch_init(int D, int K, const double* B, double* X, double* R, double* state, double rtol, double atol,
+                     int keep_xr, void* stream);
+int vt_cg_batch_update_p(int D, int K, const double* R, const double* Z, const double* minv, double* P, double* state,
+                         int maxiter, void* stream);
+int vt_cg_batch_update_xr(int D, int K, const double* P, const double* Q, double* X, double* R, double* state,
+                          void* stream);
 
 /* ---- Block-arrow Hessians (SparseBlockHessian) ------------------------------
  * H = [blockdiag(B_g) C; C^T Hgg], B_g (M x M, M <= 32), C_g (M x Dg): the

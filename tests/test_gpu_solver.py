@@ -122,3 +122,104 @@ def test_cg_solver_matrix_rhs(vt):
     assert isinstance(out, torch.Tensor) and out.is_cuda and out.shape == (d, 3)
     with pytest.raises(ValueError):
         solve(rng.normal(size=(d + 1, 3)))
+
+
+def test_cg_single_column_matrix_keeps_its_shape(vt):
+    """(dim, 1) in -> (dim, 1) out (the closure used to flatten it, which broke
+    LinearResponseCovariances(factorize_hessian=False) with one moment and a scalar hyperparameter)."""
+    rng = np.random.RandomState(3)
+    d = 24
+    a = rng.normal(size=(d, d + 2))
+    h = a @ a.T / d + np.eye(d)
+    hd = _dev(h)
+    solve = vt.solver_lib.get_cg_solver(lambda v: hd @ v if isinstance(v, torch.Tensor) else h @ v, d, {'tol': 1e-13})
+    b = rng.normal(size=(d, 1))
+    out = solve(b)
+    assert out.shape == (d, 1)
+    assert_close(out, np.linalg.solve(h, b), rtol=1e-8, atol_scale=1e-11)
+    assert solve(b[:, 0]).shape == (d,)
+    # the two call sites of the advice
+    lr = vt.LinearResponseCovariances(lambda p: 0.5 * p @ (hd @ p), np.zeros(d), factorize_hessian=False)
+    J = rng.normal(size=(1, d))
+    assert_close(lr.get_lr_covariance_from_jacobians(J, J), J @ np.linalg.solve(h, J.T), rtol=1e-7, atol_scale=1e-10)
+
+
+def test_cg_columns_stop_where_scipy_stops(vt):
+    """K right-hand sides side by side through ONE batched fused Hessian-vector product per iteration
+    (GLMObjective.vt_hvp_fn, four columns per pass over X): every column performs exactly the matrix-vector products
+    scipy's cg performs on it alone (oracle restatement of the legacy rule) and returns the same iterate."""
+    from oracle import models, solver_lib as osl
+    n, d, K = 3000, 96, 7
+    X, y, _ = models.synth_logistic(17, n, d)
+    w = np.ones(n)
+    theta = models.glm_newton(X, y, w)
+    cf = models.glm_closed_form(X, y, theta, w)
+    H = cf['hessian']
+    rng = np.random.RandomState(1)
+    B = rng.normal(size=(d, K)) * np.logspace(0, 3, K)[None, :]
+    B[:, 3] = 0.0                                            # a zero column: scipy returns it at once
+    obj = vt.objectives.GLMObjective(X, y, family='logistic')
+    hvp = obj.vt_hvp_fn(theta, w)
+    assert hvp.batched
+    assert_close(hvp(_dev(B)), H @ B, rtol=1e-10, atol_scale=1e-13)          # the batched product itself
+    for tol in (1e-5, 1e-11):
+        solve = vt.solver_lib.get_cg_solver(hvp, d, cg_opts={'tol': tol})
+        out = solve(B)
+        for k in range(K):
+            xk, info, nmv = osl.cg_reference_iterates(lambda v: H @ v, B[:, k], rtol=tol)
+            assert info == 0 and solve.iterations_per_column[k] == nmv, (k, solve.iterations_per_column, nmv)
+            assert_close(out[:, k], xk, rtol=1e-7, atol_scale=1e-9 * max(1.0, tol / 1e-11))
+        assert solve.last_iterations == max(solve.iterations_per_column)
+    # many columns: the two-GEMM form of the batched product
+    B2 = rng.normal(size=(d, 40))
+    assert_close(hvp(_dev(B2)), H @ B2, rtol=1e-10, atol_scale=1e-13)
+    sol = vt.solver_lib.get_cg_solver(hvp, d, cg_opts={'tol': 1e-12})(B2)
+    assert_close(sol, np.linalg.solve(H, B2), rtol=1e-8, atol_scale=1e-10)
+
+
+def test_cg_preconditioner_x0_and_callback(vt):
+    """cg_opts are scipy's (``solver_lib.py:70,93`` forwards them verbatim): ``M`` as a Jacobi object, a diagonal
+    sparse matrix, a dense matrix and a LinearOperator; ``x0``; ``callback``; non-convergence still warns."""
+    import scipy.sparse
+    import scipy.sparse.linalg as spla
+    rng = np.random.RandomState(5)
+    d = 60
+    a = rng.normal(size=(d, d + 5))
+    scale = np.logspace(0, 2.5, d)
+    h = (a @ a.T / d + np.eye(d)) * scale[:, None] * scale[None, :]          # badly scaled: Jacobi helps a lot
+    hd = _dev(h)
+    mv = lambda v: hd @ v if isinstance(v, torch.Tensor) else h @ v          # noqa: E731
+    b = rng.normal(size=d)
+    ref = np.linalg.solve(h, b)
+    plain = vt.solver_lib.get_cg_solver(mv, d, {'tol': 1e-10})
+    x_plain = plain(b)
+    minv = 1.0 / np.diag(h)
+    variants = {'jacobi object': vt.solver_lib.JacobiPreconditioner(np.diag(h)),
+                'sparse diagonal': scipy.sparse.diags(minv),
+                'dense diagonal': np.diag(minv),
+                'linear operator': spla.LinearOperator((d, d), matvec=lambda r: minv * r)}
+    # scipy itself with the same preconditioner (legacy rule == rtol with atol = 0)
+    x_sp, info = spla.cg(spla.LinearOperator((d, d), matvec=lambda v: h @ v), b, rtol=1e-10, atol=0.0,
+                         M=scipy.sparse.diags(minv))
+    assert info == 0
+    for name, M in variants.items():
+        solve = vt.solver_lib.get_cg_solver(mv, d, {'tol': 1e-10, 'M': M})
+        x = solve(b)
+        assert_close(x, ref, rtol=1e-6, atol_scale=1e-8, what=name)
+        assert_close(x, x_sp, rtol=1e-6, atol_scale=1e-8, what=name + ' vs scipy')
+        assert solve.last_iterations < plain.last_iterations, name
+    dense_M = np.linalg.inv(h + 0.1 * np.diag(np.diag(h)))                   # a full approximate inverse
+    s2 = vt.solver_lib.get_cg_solver(mv, d, {'tol': 1e-10, 'M': dense_M})
+    assert_close(s2(np.stack([b, 2 * b], axis=1)), np.stack([ref, 2 * ref], axis=1), rtol=1e-6, atol_scale=1e-8)
+    assert s2.last_iterations <= 12
+    # x0 = the solution: converged before the first matrix-vector product of the loop
+    s3 = vt.solver_lib.get_cg_solver(mv, d, {'tol': 1e-8, 'x0': ref})
+    assert_close(s3(b), ref, rtol=1e-8, atol_scale=1e-10)
+    assert s3.last_iterations == 0
+    seen = []
+    s4 = vt.solver_lib.get_cg_solver(mv, d, {'tol': 1e-10, 'callback': lambda xk: seen.append(np.array(xk))})
+    s4(b)
+    assert len(seen) == s4.last_iterations and np.allclose(seen[-1], x_plain)
+    with pytest.warns(UserWarning, match='CG exited with error code 3'):
+        vt.solver_lib.get_cg_solver(mv, d, {'maxiter': 3})(b)
+    assert_close(x_plain, ref, rtol=1e-6, atol_scale=1e-8)

@@ -35,6 +35,8 @@ SIGNATURES = {
     'vt_syrk_weighted': (_I, [_P, _I64, _I64, _I, _P, _D, _P, _I64, _P, _SZ, _P]),
     'vt_glm_workspace_bytes': (_SZ, [_I]),
     'vt_glm_stats': (_I, [_P, _I64, _I64, _I, _P, _P, _P, _I, _P, _P, _P, _P, _D, _P, _SZ, _P]),
+    'vt_glm_hvp_multi_workspace_bytes': (_SZ, [_I, _I]),
+    'vt_glm_hvp_multi': (_I, [_P, _I64, _I64, _I, _P, _P, _I, _D, _P, _P, _SZ, _P]),
     'vt_glm_hvp': (_I, [_P, _I64, _I64, _I, _P, _P, _D, _P, _P, _SZ, _P]),
     'vt_glm_dirderiv_workspace_bytes': (_SZ, [_I64, _I]),
     'vt_glm_dirderiv': (_I, [_P, _I64, _I64, _I, _P, _P, _I, _P, _I, _P, _P, _SZ, _P]),
@@ -57,9 +59,9 @@ SIGNATURES = {
     'vt_ij_apply_ozaki': (_I, [_P, _I64, _P, _I64, _I64, _I, _P, _P, _I64, _I, _P, _SZ, _P]),
     'vt_gemv_workspace_bytes': (_SZ, [_I, _I64]),
     'vt_gemv': (_I, [_P, _I64, _I, _I64, _P, _D, _P, _D, _P, _P, _SZ, _P]),
-    'vt_cg_init': (_I, [_I, _P, _P, _P, _P, _P]),
-    'vt_cg_update_p': (_I, [_I, _P, _P, _P, _I, _P]),
-    'vt_cg_update_xr': (_I, [_I, _P, _P, _P, _P, _P, _P]),
+    'vt_cg_batch_init': (_I, [_I, _I, _P, _P, _P, _P, _D, _D, _I, _P]),
+    'vt_cg_batch_update_p': (_I, [_I, _I, _P, _P, _P, _P, _P, _I, _P]),
+    'vt_cg_batch_update_xr': (_I, [_I, _I, _P, _P, _P, _P, _P, _P]),
     'vt_block_potrf_batched': (_I, [_P, _I64, _I, _P, _P]),
     'vt_block_trsm_batched': (_I, [_P, _P, _I64, _I, _I, _P]),
     'vt_block_trsmt_batched': (_I, [_P, _P, _I64, _I, _I, _P]),

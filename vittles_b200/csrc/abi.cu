@@ -154,6 +154,11 @@ int vt_glm_stats(const double* X, int64_t ldx, int64_t N, int D, const double* t
                    workspace_bytes, S(stream));
 }
 
+size_t vt_glm_hvp_multi_workspace_bytes(int D, int q) { return glm_hvp_multi_workspace_bytes(D, q); }
+int vt_glm_hvp_multi(const double* X, int64_t ldx, int64_t N, int D, const double* s, const double* V, int q,
+                     double ridge, double* out, void* workspace, size_t workspace_bytes, void* stream) {
+  return glm_hvp_multi(X, ldx, N, D, s, V, q, ridge, out, static_cast<double*>(workspace), workspace_bytes, S(stream));
+}
 int vt_glm_hvp(const double* X, int64_t ldx, int64_t N, int D, const double* s, const double* v, double ridge,
                double* out, void* workspace, size_t workspace_bytes, void* stream) {
   return glm_hvp(X, ldx, N, D, s, v, ridge, out, static_cast<double*>(workspace), workspace_bytes, S(stream));
@@ -280,14 +285,17 @@ int vt_gemv(const double* A, int64_t lda, int M, int64_t N, const double* x, dou
   return gemv_rows(A, lda, M, N, x, alpha, y0, beta, y, static_cast<double*>(workspace), workspace_bytes, S(stream));
 }
 
-int vt_cg_init(int D, const double* b, double* x, double* r, double* state, void* stream) {
-  return cg_init(D, b, x, r, state, S(stream));
+int vt_cg_batch_init(int D, int K, const double* B, double* X, double* R, double* state, double rtol, double atol,
+                     int keep_xr, void* stream) {
+  return cg_batch_init(D, K, B, X, R, state, rtol, atol, keep_xr, S(stream));
 }
-int vt_cg_update_p(int D, const double* r, double* p, double* state, int first, void* stream) {
-  return cg_update_p(D, r, p, state, first, S(stream));
+int vt_cg_batch_update_p(int D, int K, const double* R, const double* Z, const double* minv, double* P, double* state,
+                         int maxiter, void* stream) {
+  return cg_batch_update_p(D, K, R, Z, minv, P, state, maxiter, S(stream));
 }
-int vt_cg_update_xr(int D, const double* p, const double* q, double* x, double* r, double* state, void* stream) {
-  return cg_update_xr(D, p, q, x, r, state, S(stream));
+int vt_cg_batch_update_xr(int D, int K, const double* P, const double* Q, double* X, double* R, double* state,
+                          void* stream) {
+  return cg_batch_update_xr(D, K, P, Q, X, R, state, S(stream));
 }
 
 int vt_block_potrf_batched(double* blocks, int64_t G, int M, int32_t* info, void* stream) {

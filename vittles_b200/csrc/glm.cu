@@ -13,12 +13,12 @@
 
 namespace vt {
 
-__global__ void xtfx_reduce_kernel(const double* partial, int ncta, int Dp, int D, double* out, double alpha,
+__global__ void xtfx_reduce_kernel(const double* partial, int ncta, int stride, int D, double* out, double alpha,
                                    const double* addvec, double beta_vec) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= D) return;
   double s = 0.0;
-  for (int k = 0; k < ncta; ++k) s += partial[(size_t)k * Dp + c];
+  for (int k = 0; k < ncta; ++k) s += partial[(size_t)k * stride + c];
   s *= alpha;
   if (addvec) s += beta_vec * addvec[c];
   out[c] = s;
@@ -102,6 +102,19 @@ struct HvpOp {
   __device__ double operator()(long n, const double* t, const Aux& a) const { return a.s * t[0]; }
 };
 
+// Q Hessian-vector products in one pass: u_j = s_n (x_n . v_j)
+template <int Q>
+struct HvpMultiOp {
+  const double* s;
+  struct Aux { double s; };
+  __device__ Aux load(long n) const { return Aux{s[n]}; }
+  __device__ double operator()(long n, const double* t, const Aux& a) const { return a.s * t[0]; }
+  __device__ void multi(long n, const double* t, const Aux& a, double* u) const {
+#pragma unroll
+    for (int j = 0; j < Q; ++j) u[j] = a.s * t[j];
+  }
+};
+
 // coef[n] = w_n * b^{(k)}(z_n): elementwise pre-pass of the directional derivative
 __global__ void __launch_bounds__(256) glm_coef_kernel(const double* __restrict__ z, const double* __restrict__ w,
                                                        long N, int family, int k, const Poly poly, double* coef) {
@@ -122,27 +135,27 @@ struct DirDerivOp {
   }
 };
 
-template <class RowOp, int Q, int CPT>
+template <class RowOp, int Q, int CPT, int NOUT = 1>
 int launch_xtfx(const XtfxParams& p, const RowOp& op, cudaStream_t stream, int* grid_out) {
   constexpr int R = (CPT <= 8) ? 8 / CPT : 1;
-  constexpr int CTAS_PER_SM = (R * CPT <= 8) ? 2 : 1;
+  constexpr int CTAS_PER_SM = (R * CPT <= 8 && NOUT == 1) ? 2 : 1;
   const size_t smem = xtfx_smem_bytes(p.Dp, R, Q);
-  VT_CUDA(cudaFuncSetAttribute(xtfx_kernel<RowOp, Q, CPT, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VT_CUDA(cudaFuncSetAttribute(xtfx_kernel<RowOp, Q, CPT, R, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long nblocks = (p.N + R - 1) / R;
   const long cap = (long)num_sms() * CTAS_PER_SM;
   const int grid = (int)(nblocks < cap ? nblocks : cap);
-  xtfx_kernel<RowOp, Q, CPT, R><<<grid, XT_THREADS, smem, stream>>>(p, op);
+  xtfx_kernel<RowOp, Q, CPT, R, NOUT><<<grid, XT_THREADS, smem, stream>>>(p, op);
   VT_LAUNCH_CHECK();
   *grid_out = grid;
   return VT_OK;
 }
 
-template <class RowOp, int Q>
+template <class RowOp, int Q, int NOUT = 1>
 int dispatch_cpt(const XtfxParams& p, const RowOp& op, cudaStream_t stream, int* grid_out) {
   const int D = p.D;
-  if (D <= 512) return launch_xtfx<RowOp, Q, 1>(p, op, stream, grid_out);
-  if (D <= 1024) return launch_xtfx<RowOp, Q, 2>(p, op, stream, grid_out);
-  if (D <= 2048) return launch_xtfx<RowOp, Q, 4>(p, op, stream, grid_out);
+  if (D <= 512) return launch_xtfx<RowOp, Q, 1, NOUT>(p, op, stream, grid_out);
+  if (D <= 1024) return launch_xtfx<RowOp, Q, 2, NOUT>(p, op, stream, grid_out);
+  if (D <= 2048) return launch_xtfx<RowOp, Q, 4, NOUT>(p, op, stream, grid_out);
   if constexpr (Q == 1) {
     if (D <= 4096) return launch_xtfx<RowOp, 1, 8>(p, op, stream, grid_out);
     if (D <= 8192) return launch_xtfx<RowOp, 1, 16>(p, op, stream, grid_out);
@@ -204,6 +217,42 @@ int glm_hvp(const double* X, long ldx, long N, int D, const double* s, const dou
   xtfx_reduce_kernel<<<(D + 255) / 256, 256, 0, stream>>>(p.partial, grid, p.Dp, D, out, 1.0, v, ridge);
   VT_LAUNCH_CHECK();
   return VT_OK;
+}
+
+// out (q x D) = V X^T diag(s) X + ridge V for q <= XT_MAXQ directions (rows of V): ONE read of X for all of them.
+size_t glm_hvp_multi_workspace_bytes(int D, int q) { return glm_workspace_bytes(D) * (size_t)(q < 1 ? 1 : q); }
+
+namespace {
+template <int Q>
+int hvp_multi_q(XtfxParams& p, const double* s, const double* V, double ridge, double* out, cudaStream_t stream) {
+  HvpMultiOp<Q> op{s};
+  int grid = 0;
+  int st = dispatch_cpt<HvpMultiOp<Q>, Q, Q>(p, op, stream, &grid);
+  if (st != VT_OK) return st;
+  for (int j = 0; j < Q; ++j) {
+    xtfx_reduce_kernel<<<(p.D + 255) / 256, 256, 0, stream>>>(p.partial + (size_t)j * p.Dp, grid, Q * p.Dp, p.D,
+                                                              out + (size_t)j * p.D, 1.0, V + (size_t)j * p.D, ridge);
+    VT_LAUNCH_CHECK();
+  }
+  return VT_OK;
+}
+}  // namespace
+
+int glm_hvp_multi(const double* X, long ldx, long N, int D, const double* s, const double* V, int q, double ridge,
+                  double* out, double* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  VT_REQUIRE(s && out, "glm_hvp_multi: null pointer");
+  VT_REQUIRE(q >= 1 && q <= XT_MAXQ, "glm_hvp_multi: 1..%d directions per pass, got %d", XT_MAXQ, q);
+  VT_REQUIRE(D <= 2048 || q == 1, "glm_hvp_multi: D <= 2048 for more than one direction");
+  VT_REQUIRE(workspace && workspace_bytes >= glm_hvp_multi_workspace_bytes(D, q), "glm_hvp_multi: workspace too small");
+  if (q == 1) return glm_hvp(X, ldx, N, D, s, V, ridge, out, workspace, workspace_bytes, stream);
+  XtfxParams p;
+  int st = make_params(p, X, ldx, N, D, V, workspace, glm_workspace_bytes(D), true);
+  if (st != VT_OK) return st;
+  switch (q) {
+    case 2: return hvp_multi_q<2>(p, s, V, ridge, out, stream);
+    case 3: return hvp_multi_q<3>(p, s, V, ridge, out, stream);
+    default: return hvp_multi_q<4>(p, s, V, ridge, out, stream);
+  }
 }
 
 size_t glm_dirderiv_workspace_bytes(long N, int D) { return glm_workspace_bytes(D) + (size_t)N * 8; }
@@ -311,13 +360,16 @@ int gemv_rows(const double* A, long lda, int M, long N, const double* x, double 
 }
 
 // ---------------------------------------------------------------------------
-// Conjugate-gradient vector kernels.  The iteration follows scipy's cg
-// (the reference's solver, solver_lib.py:91-97) step for step so that the
-// iteration count matches; all scalars stay on the device:
-//   state = {rho, rho_prev, pq, rnorm2}
-//   cg_update_p : rho = r.r (computed by previous kernel), p = r + (rho/rho_prev) p
-//   cg_update_xr: alpha = rho / (p.q);  x += alpha p;  r -= alpha q;  rnorm2 = r.r
-// Single-CTA kernels: D is at most a few thousand, so one block of 1024 threads
+// Conjugate-gradient vector kernels, batched over K right-hand sides.  Every column runs scipy's cg (the reference's
+// solver, solver_lib.py:91-97, legacy stopping rule) step for step on its own scalars, so that each column stops at
+// the iteration scipy would stop at; the columns only share the matrix-vector product (one fused pass over X for
+// up to four of them).  All scalars stay on the device - the host never reads a residual norm:
+//   state[k] = {rho, rho_prev, p.q, |r|^2, |b|^2, tol, status, matvecs}     status 1: running, 0: converged,
+//                                                                           2: stopped at maxiter
+//   cg_batch_update_p : if |r| < tol: status 0.  else z = M r (z given, or minv .* r, or r), rho = r.z,
+//                       p = z + (rho / rho_prev) p.  Columns that are not running get p = 0.
+//   cg_batch_update_xr: alpha = rho / (p.q);  x += alpha p;  r -= alpha q;  |r|^2
+// Vectors are rows of (K, D) arrays.  One CTA of 1024 threads per column: D is at most a few thousand, so one block
 // does the vector update and the deterministic reduction in one launch.
 // ---------------------------------------------------------------------------
 namespace {
@@ -338,34 +390,90 @@ __device__ double block_sum_1024(double v, double* red) {
   return t;
 }
 
-// state[0]=rho, [1]=rho_prev, [2]=pq, [3]=rnorm2, [4]=bnorm2
-__global__ void __launch_bounds__(1024) cg_init_kernel(int D, const double* b, double* x, double* r, double* state) {
+constexpr int CG_RHO = 0, CG_RHO_PREV = 1, CG_PQ = 2, CG_RNORM2 = 3, CG_BNORM2 = 4, CG_TOL = 5, CG_STATUS = 6, CG_ITERS = 7;
+
+__global__ void __launch_bounds__(1024) cg_batch_init_kernel(int D, const double* B, double* X, double* R, double* state,
+                                                             double rtol, double atol, int keep_xr) {
   __shared__ double red[32];
-  double s = 0.0;
+  const long off = (long)blockIdx.x * D;
+  const double* b = B + off;
+  double* x = X + off;
+  double* r = R + off;
+  double* st = state + 8L * blockIdx.x;
+  double sb = 0.0, sr = 0.0;
   for (int i = threadIdx.x; i < D; i += blockDim.x) {
     const double bi = b[i];
-    x[i] = 0.0;
-    r[i] = bi;
-    s = fma(bi, bi, s);
+    if (!keep_xr) { x[i] = 0.0; r[i] = bi; }
+    const double ri = r[i];
+    sb = fma(bi, bi, sb);
+    sr = fma(ri, ri, sr);
   }
-  s = block_sum_1024(s, red);
-  if (threadIdx.x == 0) { state[0] = s; state[1] = 0.0; state[2] = 0.0; state[3] = s; state[4] = s; }
+  sb = block_sum_1024(sb, red);
+  sr = block_sum_1024(sr, red);
+  if (threadIdx.x == 0) {
+    const double bn = sqrt(sb);
+    st[CG_RHO] = 0.0; st[CG_RHO_PREV] = 0.0; st[CG_PQ] = 0.0;
+    st[CG_RNORM2] = sr; st[CG_BNORM2] = sb;
+    st[CG_TOL] = fmax(atol, rtol * bn);
+    st[CG_STATUS] = (sb == 0.0) ? 0.0 : 1.0;       // scipy: a zero right-hand side returns x = b at once
+    st[CG_ITERS] = 0.0;
+  }
+  if (sb == 0.0 && !keep_xr) return;
+  if (sb == 0.0)
+    for (int i = threadIdx.x; i < D; i += blockDim.x) x[i] = 0.0;
 }
 
-__global__ void __launch_bounds__(1024) cg_update_p_kernel(int D, const double* r, double* p, double* state, int first) {
-  const double rho = state[3];   // r.r of the current residual
-  const double beta = first ? 0.0 : rho / state[1];
-  for (int i = threadIdx.x; i < D; i += blockDim.x) p[i] = first ? r[i] : fma(beta, p[i], r[i]);
-  if (threadIdx.x == 0) state[0] = rho;
-}
-
-__global__ void __launch_bounds__(1024) cg_update_xr_kernel(int D, const double* p, const double* q, double* x,
-                                                             double* r, double* state) {
+__global__ void __launch_bounds__(1024) cg_batch_update_p_kernel(int D, const double* R, const double* Zin,
+                                                                 const double* minv, double* P, double* state,
+                                                                 int maxiter) {
   __shared__ double red[32];
+  const long off = (long)blockIdx.x * D;
+  const double* r = R + off;
+  double* p = P + off;
+  double* st = state + 8L * blockIdx.x;
+  double status = st[CG_STATUS];
+  const double iters = st[CG_ITERS];
+  if (status == 1.0) {
+    if (sqrt(st[CG_RNORM2]) < st[CG_TOL]) status = 0.0;
+    else if (iters >= (double)maxiter) status = 2.0;
+  }
+  if (status != 1.0) {
+    for (int i = threadIdx.x; i < D; i += blockDim.x) p[i] = 0.0;
+    if (threadIdx.x == 0) st[CG_STATUS] = status;
+    return;
+  }
+  const double* z = Zin ? Zin + off : nullptr;
+  double rho;
+  if (z || minv) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) s = fma(r[i], z ? z[i] : minv[i] * r[i], s);
+    rho = block_sum_1024(s, red);
+  } else {
+    rho = st[CG_RNORM2];
+  }
+  const bool first = iters == 0.0;
+  const double beta = first ? 0.0 : rho / st[CG_RHO_PREV];
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    const double zi = z ? z[i] : (minv ? minv[i] * r[i] : r[i]);
+    p[i] = first ? zi : fma(beta, p[i], zi);
+  }
+  if (threadIdx.x == 0) { st[CG_RHO] = rho; st[CG_ITERS] = iters + 1.0; }
+}
+
+__global__ void __launch_bounds__(1024) cg_batch_update_xr_kernel(int D, const double* P, const double* Q, double* X,
+                                                                  double* R, double* state) {
+  __shared__ double red[32];
+  const long off = (long)blockIdx.x * D;
+  double* st = state + 8L * blockIdx.x;
+  if (st[CG_STATUS] != 1.0) return;
+  const double* p = P + off;
+  const double* q = Q + off;
+  double* x = X + off;
+  double* r = R + off;
   double s = 0.0;
   for (int i = threadIdx.x; i < D; i += blockDim.x) s = fma(p[i], q[i], s);
   const double pq = block_sum_1024(s, red);
-  const double rho = state[0];
+  const double rho = st[CG_RHO];
   const double alpha = rho / pq;
   double rr = 0.0;
   for (int i = threadIdx.x; i < D; i += blockDim.x) {
@@ -375,23 +483,28 @@ __global__ void __launch_bounds__(1024) cg_update_xr_kernel(int D, const double*
     rr = fma(ri, ri, rr);
   }
   rr = block_sum_1024(rr, red);
-  if (threadIdx.x == 0) { state[1] = rho; state[2] = pq; state[3] = rr; }
+  if (threadIdx.x == 0) { st[CG_RHO_PREV] = rho; st[CG_PQ] = pq; st[CG_RNORM2] = rr; }
 }
 }  // namespace
 
-int cg_init(int D, const double* b, double* x, double* r, double* state, cudaStream_t stream) {
-  VT_REQUIRE(D >= 1 && b && x && r && state, "cg_init: bad arguments");
-  cg_init_kernel<<<1, 1024, 0, stream>>>(D, b, x, r, state);
+int cg_batch_init(int D, int K, const double* B, double* X, double* R, double* state, double rtol, double atol,
+                  int keep_xr, cudaStream_t stream) {
+  VT_REQUIRE(D >= 1 && K >= 1 && B && X && R && state, "cg_batch_init: bad arguments");
+  cg_batch_init_kernel<<<K, 1024, 0, stream>>>(D, B, X, R, state, rtol, atol, keep_xr);
   VT_LAUNCH_CHECK();
   return VT_OK;
 }
-int cg_update_p(int D, const double* r, double* p, double* state, int first, cudaStream_t stream) {
-  cg_update_p_kernel<<<1, 1024, 0, stream>>>(D, r, p, state, first);
+int cg_batch_update_p(int D, int K, const double* R, const double* Z, const double* minv, double* P, double* state,
+                      int maxiter, cudaStream_t stream) {
+  VT_REQUIRE(D >= 1 && K >= 1 && R && P && state && maxiter >= 0, "cg_batch_update_p: bad arguments");
+  cg_batch_update_p_kernel<<<K, 1024, 0, stream>>>(D, R, Z, minv, P, state, maxiter);
   VT_LAUNCH_CHECK();
   return VT_OK;
 }
-int cg_update_xr(int D, const double* p, const double* q, double* x, double* r, double* state, cudaStream_t stream) {
-  cg_update_xr_kernel<<<1, 1024, 0, stream>>>(D, p, q, x, r, state);
+int cg_batch_update_xr(int D, int K, const double* P, const double* Q, double* X, double* R, double* state,
+                       cudaStream_t stream) {
+  VT_REQUIRE(D >= 1 && K >= 1 && P && Q && X && R && state, "cg_batch_update_xr: bad arguments");
+  cg_batch_update_xr_kernel<<<K, 1024, 0, stream>>>(D, P, Q, X, R, state);
   VT_LAUNCH_CHECK();
   return VT_OK;
 }

@@ -19,6 +19,11 @@ int glm_stats(const double* X, long ldx, long N, int D, const double* theta, con
 int glm_hvp(const double* X, long ldx, long N, int D, const double* s, const double* v, double ridge, double* out,
             double* workspace, size_t workspace_bytes, cudaStream_t stream);
 
+// out (q x D) = V X^T diag(s) X + ridge V for q <= 4 directions (rows of V) in ONE pass over X
+size_t glm_hvp_multi_workspace_bytes(int D, int q);
+int glm_hvp_multi(const double* X, long ldx, long N, int D, const double* s, const double* V, int q, double ridge,
+                  double* out, double* workspace, size_t workspace_bytes, cudaStream_t stream);
+
 // out = X^T ( w .* b^{(q+1)}(z) .* prod_j (X dirs_j) ),  dirs is (q, D) row-major
 size_t glm_dirderiv_workspace_bytes(long N, int D);
 int glm_dirderiv(const double* X, long ldx, long N, int D, const double* z, const double* w, int family,
@@ -30,8 +35,12 @@ size_t gemv_workspace_bytes(int M, long N);
 int gemv_rows(const double* A, long lda, int M, long N, const double* x, double alpha, const double* y0, double beta,
               double* y, double* workspace, size_t workspace_bytes, cudaStream_t stream);
 
-int cg_init(int D, const double* b, double* x, double* r, double* state, cudaStream_t stream);
-int cg_update_p(int D, const double* r, double* p, double* state, int first, cudaStream_t stream);
-int cg_update_xr(int D, const double* p, const double* q, double* x, double* r, double* state, cudaStream_t stream);
+// K conjugate-gradient iterations side by side (rows of (K, D) arrays; state is K x 8 doubles), see glm.cu
+int cg_batch_init(int D, int K, const double* B, double* X, double* R, double* state, double rtol, double atol,
+                  int keep_xr, cudaStream_t stream);
+int cg_batch_update_p(int D, int K, const double* R, const double* Z, const double* minv, double* P, double* state,
+                      int maxiter, cudaStream_t stream);
+int cg_batch_update_xr(int D, int K, const double* P, const double* Q, double* X, double* R, double* state,
+                       cudaStream_t stream);
 
 }  // namespace vt

@@ -4,6 +4,7 @@
 // by HBM at 8*N*D bytes.  Instances:
 //   * GLM statistics + gradient      (Q=1, v=theta; writes z, resid, s)
 //   * Hessian-vector product         (Q=1; u = s_n * t)            -> CG solver
+//   * Q Hessian-vector products      (Q=NOUT<=4; u_j = s_n * t_j)  -> multi-RHS CG: one read of X for Q columns
 //   * Taylor directional derivatives (Q=m; u = c_n * prod_j t_j)   -> dirderiv
 //
 // Structure (B200): persistent CTAs, two per SM, 256 threads.  A block of
@@ -28,7 +29,7 @@ constexpr int XT_MAXQ = 4;
 struct XtfxParams {
   const double* X; long ldx; long N; int D;
   const double* V;        // Q x D directions, row-major, contiguous
-  double* partial;        // [grid][Dp] column sums per CTA (null: skip the transposed pass)
+  double* partial;        // [grid][NOUT][Dp] column sums per CTA (null: skip the transposed pass)
   int Dp;                 // D rounded up to even
   int bulk;               // 1: rows can be staged with cp.async.bulk
   int contiguous;         // 1: ldx == D, a block of rows is one contiguous copy
@@ -67,21 +68,23 @@ __device__ __forceinline__ void fence_barrier_init() {
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 inline size_t xtfx_smem_bytes(int Dp, int R, int Q) {
-  return (size_t)XT_NBUF * R * Dp * 8 + (size_t)(8 * R * Q + R) * 8 + XT_NBUF * 8 + 128;
+  return (size_t)XT_NBUF * R * Dp * 8 + (size_t)(8 * R * Q + R * Q) * 8 + XT_NBUF * 8 + 128;
 }
 
 // R rows per block, CPT double2 columns per thread: R*CPT = 8 gives 32 KB blocks at
 // D = 512*CPT, a 96 KB ring and two CTAs per SM, so that the block-wide syncs and
 // the serial row-functor step of one CTA overlap the other's arithmetic (one
 // CTA per SM left stats at 62% and the HVP at 79% of HBM peak, profiles/r01).
-template <class RowOp, int Q, int CPT, int R>
-__global__ void __launch_bounds__(XT_THREADS, (R * CPT <= 8) ? 2 : 1) xtfx_kernel(const XtfxParams p, const RowOp op) {
+// NOUT = 1: one output vector, u_n = op(n, t, aux).  NOUT = Q > 1: Q output vectors, op.multi(n, t, aux, u) fills
+// u_j - the accumulators of all Q outputs live in registers, so the CTA count per SM drops to one.
+template <class RowOp, int Q, int CPT, int R, int NOUT = 1>
+__global__ void __launch_bounds__(XT_THREADS, (R * CPT <= 8 && NOUT == 1) ? 2 : 1) xtfx_kernel(const XtfxParams p, const RowOp op) {
   extern __shared__ __align__(128) unsigned char xt_raw[];
   const int Dp = p.Dp;
   double* bufs = reinterpret_cast<double*>(xt_raw);
   double* s_part = bufs + (size_t)XT_NBUF * R * Dp;   // [8][R][Q]
-  double* s_u = s_part + 8 * R * Q;                    // [R]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_u + R);
+  double* s_u = s_part + 8 * R * Q;                    // [R][NOUT]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_u + R * Q);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long nblocks = (p.N + R - 1) / R;
@@ -118,9 +121,11 @@ __global__ void __launch_bounds__(XT_THREADS, (R * CPT <= 8) ? 2 : 1) xtfx_kerne
       v[j][i].x = (c < p.D) ? p.V[(long)j * p.D + c] : 0.0;
       v[j][i].y = (c + 1 < p.D) ? p.V[(long)j * p.D + c + 1] : 0.0;
     }
-  double2 acc[CPT];
+  double2 acc[NOUT][CPT];
 #pragma unroll
-  for (int i = 0; i < CPT; ++i) acc[i] = make_double2(0.0, 0.0);
+  for (int o = 0; o < NOUT; ++o)
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) acc[o][i] = make_double2(0.0, 0.0);
 
   if (p.bulk && tid == 0) {
     for (int s = 0; s < XT_NBUF; ++s) {
@@ -186,34 +191,47 @@ __global__ void __launch_bounds__(XT_THREADS, (R * CPT <= 8) ? 2 : 1) xtfx_kerne
         for (int w = 0; w < 8; ++w) s += s_part[(w * R + tid) * Q + j];
         t[j] = s;
       }
-      s_u[tid] = (tid < rows) ? op(row0 + tid, t, aux) : 0.0;
+      if constexpr (NOUT == 1) {
+        s_u[tid] = (tid < rows) ? op(row0 + tid, t, aux) : 0.0;
+      } else {
+        double u[NOUT];
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) u[o] = 0.0;
+        if (tid < rows) op.multi(row0 + tid, t, aux, u);
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) s_u[tid * NOUT + o] = u[o];
+      }
     }
     if (p.partial) {
       __syncthreads();
       // ---- phase 2: rank-R update of the column sums --------------------
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const double u = s_u[r];
+      for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int i = 0; i < CPT; ++i) {
-          acc[i].x = fma(u, x[r][i].x, acc[i].x);
-          acc[i].y = fma(u, x[r][i].y, acc[i].y);
+        for (int o = 0; o < NOUT; ++o) {
+          const double u = s_u[r * NOUT + o];
+#pragma unroll
+          for (int i = 0; i < CPT; ++i) {
+            acc[o][i].x = fma(u, x[r][i].x, acc[o][i].x);
+            acc[o][i].y = fma(u, x[r][i].y, acc[o][i].y);
+          }
         }
-      }
     }
     // s_part / s_u are rewritten only after the next block's first barrier
   }
   if (p.partial) {
 #pragma unroll
-    for (int i = 0; i < CPT; ++i) {
-      const int c = 2 * tid + 512 * i;
-      if (c < Dp) *reinterpret_cast<double2*>(p.partial + (size_t)blockIdx.x * Dp + c) = acc[i];
-    }
+    for (int o = 0; o < NOUT; ++o)
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) {
+        const int c = 2 * tid + 512 * i;
+        if (c < Dp) *reinterpret_cast<double2*>(p.partial + ((size_t)blockIdx.x * NOUT + o) * Dp + c) = acc[o][i];
+      }
   }
 }
 
-// out[c] = alpha * sum_cta partial[cta][c] + beta_vec * addvec[c]
-__global__ void xtfx_reduce_kernel(const double* partial, int ncta, int Dp, int D, double* out, double alpha,
+// out[c] = alpha * sum_cta partial[cta * stride + c] + beta_vec * addvec[c]
+__global__ void xtfx_reduce_kernel(const double* partial, int ncta, int stride, int D, double* out, double alpha,
                                    const double* addvec, double beta_vec);
 
 }  // namespace vt

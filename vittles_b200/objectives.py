@@ -219,11 +219,17 @@ class GLMObjective(StructuredObjective):
         s = self.vt_stats(theta, w, want_grad=False)['s']
 
         def hvp(v):
-            out = ops.glm_hvp(self.X, s, to_device(v, self.X.device), ridge=0.0)
+            """(D,) -> (D,), or (D, K) -> (D, K): the K columns share the passes over X (four per fused pass)."""
+            v = to_device(v, self.X.device)
+            if v.dim() == 2:
+                out = ops.glm_hvp_multi(self.X, s, v.T.contiguous(), ridge=0.0).T.contiguous()
+            else:
+                out = ops.glm_hvp(self.X, s, v, ridge=0.0)
             self._allreduce(out)
             if self.l2 != 0.0:
-                out = out + self.l2 * to_device(v, self.X.device)
+                out = out + self.l2 * v
             return out
+        hvp.batched = True
         return hvp
 
     def vt_directional_derivative(self, theta, w, eta_dirs, eps_dirs, cache=None):
@@ -289,11 +295,16 @@ class GLMPriorObjective(StructuredObjective):
         s = self._glm.vt_stats(theta, None, want_grad=False)['s']
 
         def hvp(v):
+            """(D,) -> (D,), or (D, K) -> (D, K): the K columns share the passes over X (four per fused pass)."""
             v = to_device(v, self.X.device)
+            if v.dim() == 2:
+                out = self._allreduce(ops.glm_hvp_multi(self.X, s, v.T.contiguous(), ridge=0.0).T.contiguous())
+                return out + tau * v
             if self.group is None:
                 return ops.glm_hvp(self.X, s, v, ridge=tau)
             out = self._allreduce(ops.glm_hvp(self.X, s, v, ridge=0.0))
             return out + tau * v
+        hvp.batched = True
         return hvp
 
     def vt_directional_derivative(self, theta, eps, eta_dirs, eps_dirs, cache=None):

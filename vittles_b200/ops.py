@@ -47,7 +47,7 @@ def _f64(t, name):
 
 def _mat(t, name):
     _f64(t, name)
-    if t.dim() != 2 or t.stride(1) != 1:
+    if t.dim() != 2 or (t.stride(1) != 1 and t.shape[1] > 1):       # (the stride of a length-1 dimension is arbitrary)
         raise ValueError('{} must be a row-major 2-d tensor (unit stride in the last dimension)'.format(name))
     return t
 
@@ -303,6 +303,37 @@ def glm_hvp(X, s, v, ridge=0.0, out=None):
     return out
 
 
+HVP_MULTI_MAX = 4            # directions per pass of the fused kernel (XT_MAXQ)
+HVP_GEMM_MIN = 24            # from this many directions on, two GEMMs (X read twice) beat ceil(K / 4) fused passes
+
+
+def glm_hvp_multi(X, s, V, ridge=0.0):
+    """out (K, D) = V X^T diag(s) X + ridge V for the K rows of V.  Up to four directions share ONE fused pass over X
+    (vt_glm_hvp_multi); many directions go through the FP64 GEMM engine: T = diag(s) X V^T (N, K) and out = T^T X,
+    two reads of X whatever K is."""
+    lib = _cabi.require_cuda()
+    _mat(X, 'X')
+    V = _mat(_f64(V, 'V').contiguous(), 'V')
+    N, D = X.shape
+    K = V.shape[0]
+    if V.shape[1] != D:
+        raise ValueError('V must have shape (K, D)')
+    s = _f64(s, 's').contiguous()
+    if K >= HVP_GEMM_MIN or (K > 1 and D > 2048):
+        T = gemm(X, V, 'KC', 'KC', rowscale=s)                  # (N, K) = diag(s) X V^T
+        out = gemm(T, X, 'KS', 'KS')                            # (K, D) = T^T X
+        if ridge != 0.0:
+            out.add_(V, alpha=float(ridge))
+        return out
+    out = torch.empty((K, D), dtype=torch.float64, device=X.device)
+    ws, wsb = _ws('glm_multi', lib.vt_glm_hvp_multi_workspace_bytes(D, min(K, HVP_MULTI_MAX)), X.device)
+    for k0 in range(0, K, HVP_MULTI_MAX):
+        q = min(HVP_MULTI_MAX, K - k0)
+        check(lib.vt_glm_hvp_multi(ptr(X), _ld(X), N, D, ptr(s), ptr(V[k0:k0 + q]), q, float(ridge), ptr(out[k0:k0 + q]),
+                                   ptr(ws), wsb, stream()))
+    return out
+
+
 def glm_dirderiv(X, z, dirs, w=None, family='logistic', out=None):
     """out = X^T ( w .* b^{(q+1)}(z) .* prod_j X dirs[j] ) for dirs of shape (q, D)."""
     lib = _cabi.require_cuda()
@@ -424,16 +455,22 @@ def gemv(A, x, alpha=1.0, y0=None, beta=1.0):
 
 
 # -------------------------------------------------------------------- CG ----
-def cg_init(b, x, r, state):
-    check(_cabi.require_cuda().vt_cg_init(b.numel(), ptr(b), ptr(x), ptr(r), ptr(state), stream()))
+def cg_batch_init(B, X, R, state, rtol, atol, keep_xr=False):
+    """B, X, R: (K, D) rows; state (K, 8).  See include/vittles_b200.h."""
+    K, D = B.shape
+    check(_cabi.require_cuda().vt_cg_batch_init(D, K, ptr(B), ptr(X), ptr(R), ptr(state), float(rtol), float(atol),
+                                                int(bool(keep_xr)), stream()))
 
 
-def cg_update_p(r, p, state, first):
-    check(_cabi.require_cuda().vt_cg_update_p(r.numel(), ptr(r), ptr(p), ptr(state), int(first), stream()))
+def cg_batch_update_p(R, P, state, maxiter, Z=None, minv=None):
+    K, D = R.shape
+    check(_cabi.require_cuda().vt_cg_batch_update_p(D, K, ptr(R), ptr(Z), ptr(minv), ptr(P), ptr(state), int(maxiter),
+                                                    stream()))
 
 
-def cg_update_xr(p, q, x, r, state):
-    check(_cabi.require_cuda().vt_cg_update_xr(p.numel(), ptr(p), ptr(q), ptr(x), ptr(r), ptr(state), stream()))
+def cg_batch_update_xr(P, Q, X, R, state):
+    K, D = P.shape
+    check(_cabi.require_cuda().vt_cg_batch_update_xr(D, K, ptr(P), ptr(Q), ptr(X), ptr(R), ptr(state), stream()))
 
 
 # ------------------------------------------------------------- synthetic ----
@@ -575,7 +612,8 @@ def _device_scoped(fn):
 
 
 for _name in ('gemm', 'tf32_convert', 'tf32_gemm', 'ozaki_slice', 'ozaki_gemm', 'syrk_weighted', 'glm_stats', 'glm_hvp',
-              'glm_dirderiv', 'potrf', 'ij_apply', 'gemv', 'cg_init', 'cg_update_p', 'cg_update_xr', 'synth_design',
+              'glm_hvp_multi', 'glm_dirderiv', 'potrf', 'ij_apply', 'gemv', 'cg_batch_init', 'cg_batch_update_p', 'cg_batch_update_xr',
+              'synth_design',
               'synth_theta', 'synth_bernoulli', 'block_potrf', 'block_trsm', 'block_solve', 'tall_gemv', 'tall_colsum',
               'gmm_blocks'):
     globals()[_name] = _device_scoped(globals()[_name])

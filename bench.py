@@ -33,6 +33,7 @@ import numpy as np  # noqa: E402
 METRIC = 'per-obs IJ sensitivities/sec (logit N=10M,D=1024)'
 UNIT = 'obs/s'
 SEED = 20261017
+ORIG_AFFINITY = os.sched_getaffinity(0) if hasattr(os, 'sched_getaffinity') else None
 FP64_PEAK_FALLBACK_TFLOPS = 37.18      # profiles/fp64_peak_r01.jsonl (tools/fp64_peak.cu on this pool's B200)
 
 
@@ -48,11 +49,13 @@ def parse():
                     help='rows of the CPU-baseline sample (0: sized from a calibration run, 1e5 .. 1e6 rows)')
     ap.add_argument('--e2e-steps', type=int, default=2)
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-e2e-full', action='store_true', help='skip the leg that also brings the (D, N) result to the host')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-tf32', action='store_true', help='skip the rows of the other engines (f64 DMMA, tf32x3, tf32)')
     ap.add_argument('--precision', default='auto', choices=['auto', 'f64', 'f64_ozaki', 'tf32x3', 'tf32'],
                     help="engine of the two contractions for the headline and e2e legs (default 'auto': the library's "
                          "default, which is the FP64-grade INT8 error-free-slicing engine at this size)")
+    ap.add_argument('--no-configs', action='store_true', help='skip BASELINE configs 3, 4, 5 (tools/bench_configs.py)')
     ap.add_argument('--engine-rows-only', action='store_true', help=argparse.SUPPRESS)   # child mode, see main()
     ap.add_argument('--engines', action='store_true', help='also measure the other engines when --gpus > 1 '
                     '(by default they are measured on 1 GPU only)')
@@ -86,6 +89,8 @@ def use_all_host_cores():
     """BLAS threads := all host cores, whatever OMP_NUM_THREADS says (torch.distributed.run exports
     OMP_NUM_THREADS=1 to its workers, which made the r01 reference arm single-threaded at N > 1).  Returns the
     number of threads the BLAS pool now uses."""
+    if hasattr(os, 'sched_setaffinity'):
+        os.sched_setaffinity(0, ORIG_AFFINITY)      # undo the NUMA binding of the GPU legs
     ncores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
     try:
         from threadpoolctl import threadpool_limits, threadpool_info
@@ -219,6 +224,7 @@ def main():
         raise SystemExit('--gpus {} but WORLD_SIZE={}'.format(args.gpus, world))
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    numa_note = numa_bind_to_gpu(local_rank)      # before any pinned allocation: first touch places the pages
     group = None
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
@@ -364,7 +370,7 @@ def main():
         pass
 
     # ---- end to end: HOST buffers in, host result out ---------------------------
-    e2e = None
+    e2e = e2e_full = None
     freed = False
     if not args.no_e2e:
         try:
@@ -376,9 +382,15 @@ def main():
             ops.free_workspaces()
             torch.cuda.empty_cache()
             e2e = run_e2e(args, vt, torch, dist, dev, group, world, host)
+            e2e['numa'] = numa_note
         except Exception as exc:      # report, never hide
             e2e = {'value': None, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0,
                    'error': repr(exc)[:300]}
+        if e2e.get('value') and not args.no_e2e_full:
+            try:
+                e2e_full = run_e2e(args, vt, torch, dist, dev, group, world, host, full=True)
+            except Exception as exc:      # report, never hide (e.g. not enough pinnable host memory for X and S)
+                e2e_full = {'value': None, 'unit': UNIT, 'error': repr(exc)[:300]}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -395,12 +407,13 @@ def main():
         if not freed:
             obj.X = obj.y = obj = None
             del X, y, st, H, hinv, w
+            freed = True
         host = None
         ops.free_workspaces()
         gc.collect()
         torch.cuda.empty_cache()
         cmd = [sys.executable, os.path.abspath(__file__), '--engine-rows-only', '--n-total', str(N), '--dim', str(D),
-               '--steps', str(min(args.steps, 3)), '--warmup', '1', '--no-e2e', '--no-cpu-baseline',
+               '--steps', str(min(args.steps, 3)), '--warmup', '1', '--no-e2e', '--no-cpu-baseline', '--no-configs',
                '--precision', args.precision]
         try:
             child = subprocess.run(cmd, capture_output=True, text=True, timeout=1500)
@@ -409,6 +422,26 @@ def main():
                 'error': 'child exited with code {}: {}'.format(child.returncode, child.stderr[-300:])}
         except Exception as exc:              # report, never hide
             engine_rows = {'error': repr(exc)[:300]}
+
+    # ---- BASELINE configs 3, 4, 5 (block-arrow factorisation, dense LR covariance, Taylor + CG), measured by the
+    # same driver-run command on the same ranks; every device tensor of the headline legs is gone by now
+    configs = None
+    if not args.no_configs:
+        try:
+            import gc
+            if not freed:
+                obj.X = obj.y = obj = None
+                del X, y, st, H, hinv, w
+                freed = True
+            host = None
+            ops.free_workspaces()
+            gc.collect()
+            torch.cuda.empty_cache()
+            sys.path.insert(0, os.path.join(ROOT, 'tools'))
+            import bench_configs
+            configs = bench_configs.run_all(dev, group, peak=peak_tflops)
+        except Exception as exc:              # report, never hide
+            configs = {'error': repr(exc)[:300]}
 
     if rank == 0:
         S_ = ops.OZAKI_SLICES
@@ -469,7 +502,9 @@ def main():
             },
             'cpu_baseline': cpu_baseline,
             'e2e': e2e,
+            'e2e_full': e2e_full,
             'other_engines': engine_rows,
+            'configs': configs,
         }
         print(json.dumps(line))
     if world > 1:
@@ -531,18 +566,49 @@ def stage_to_host(torch, X, y, theta):
     return dict(X=X_host, y=y_host, w=w_host, w1=w1.pin_memory(), theta=theta.cpu().pin_memory())
 
 
-def run_e2e(args, vt, torch, dist, dev, group, world, host):
+def numa_bind_to_gpu(local_rank):
+    """Run this process (and first-touch its pinned staging memory) on the host NUMA node of its GPU, when the box
+    exposes more than one node.  Returns a short description for the report."""
+    try:
+        nodes = [d for d in os.listdir('/sys/devices/system/node') if d.startswith('node') and d[4:].isdigit()]
+        if len(nodes) < 2:
+            return '{} NUMA node visible: nothing to bind'.format(len(nodes))
+        import subprocess as sp
+        q = sp.run(['nvidia-smi', '-i', str(local_rank), '--query-gpu=pci.bus_id', '--format=csv,noheader'],
+                   capture_output=True, text=True).stdout.strip().lower()
+        dom = q[4:] if q.startswith('0000') and len(q) > 12 else q          # 00000000:1B:00.0 -> 0000:1b:00.0
+        with open('/sys/bus/pci/devices/{}/numa_node'.format(dom)) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return 'GPU {} reports no NUMA node'.format(local_rank)
+        with open('/sys/devices/system/node/node{}/cpulist'.format(node)) as f:
+            cpus = set()
+            for part in f.read().strip().split(','):
+                lo, _, hi = part.partition('-')
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return 'NUMA node {} of GPU {} has no CPU this process may use'.format(node, local_rank)
+        os.sched_setaffinity(0, allowed)
+        return 'bound to NUMA node {} ({} CPUs) of GPU {}'.format(node, len(allowed), local_rank)
+    except Exception as exc:
+        return 'not bound: {!r}'.format(exc)[:160]
+
+
+def run_e2e(args, vt, torch, dist, dev, group, world, host, full=False):
     """The same metric through the public API with HOST buffers: every step
     copies this rank's X, y, w and theta from pinned host memory to the device,
     runs the whole path, and reads the result summary (the linear-approximation
     prediction for a leave-k-out weight vector, D doubles, plus the D x D
-    Hessian) back to the host.  The (D, N) sensitivity matrix itself stays on
-    the device, as a user of an 82 GB result would keep it."""
+    Hessian) back to the host.  full=False: the (D, N) sensitivity matrix itself
+    stays on the device, as a user of an 82 GB result would keep it.  full=True:
+    get_dopt_dhyper() is called as well and returns the whole matrix on the HOST
+    (what the reference's get_dopt_dhyper returns, sensitivity_lib.py:230-231)."""
     X_host, y_host, w_host, w1_host, theta_host = host['X'], host['y'], host['w'], host['w1'], host['theta']
     n_loc, D = X_host.shape
     N = args.n_total
     h2d = (X_host.numel() + y_host.numel() + 2 * w_host.numel() + theta_host.numel()) * 8
-    d2h = (D + D * D) * 8
+    d2h = (D + D * D) * 8 + (D * n_loc * 8 if full else 0)
 
     def step():
         # host (pinned) buffers straight into the public API: GLMObjective starts chunked
@@ -552,6 +618,10 @@ def run_e2e(args, vt, torch, dist, dev, group, world, host):
         pred = sens.predict_opt_par_from_hyper_par(w1_host)      # D doubles, returned on the host
         hess = sens.get_hessian_at_opt()                         # D x D, returned on the host
         assert not pred.is_cuda and not hess.is_cuda
+        if full:
+            S_host = sens.get_dopt_dhyper()                      # (D, n_loc) on the host (pinned staging)
+            assert not S_host.is_cuda and tuple(S_host.shape) == (D, n_loc)
+            return pred, hess, S_host
         return pred, hess
 
     def barrier():
@@ -572,10 +642,29 @@ def run_e2e(args, vt, torch, dist, dev, group, world, host):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_step = float(ms.item()) / args.e2e_steps
-    return {'value': N / (ms_step * 1e-3), 'unit': UNIT, 'ms_per_step': ms_step, 'steps': args.e2e_steps,
-            'h2d_bytes_per_step': h2d * world, 'd2h_bytes_per_step': d2h * world,
-            'api': 'HyperparameterSensitivityLinearApproximation(GLMObjective(host X, host y), theta, w)'
-                   '.predict_opt_par_from_hyper_par(w1) + get_hessian_at_opt()'}
+    res = {'value': N / (ms_step * 1e-3), 'unit': UNIT, 'ms_per_step': ms_step, 'steps': args.e2e_steps,
+           'h2d_bytes_per_step': h2d * world, 'd2h_bytes_per_step': d2h * world,
+           'api': 'HyperparameterSensitivityLinearApproximation(GLMObjective(host X, host y), theta, w)'
+                  '.predict_opt_par_from_hyper_par(w1) + get_hessian_at_opt()' + (' + get_dopt_dhyper() -> host' if full else '')}
+    if not full:
+        # the bound of this leg: every rank's bare pinned H2D copy of its shard of X, all ranks at once
+        Xd = torch.empty((n_loc, D), dtype=torch.float64, device=dev)
+        Xd.copy_(X_host, non_blocking=True)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        Xd.copy_(X_host, non_blocking=True)
+        c1.record()
+        barrier()
+        cms = torch.tensor([c0.elapsed_time(c1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(cms, op=dist.ReduceOp.MAX)
+        del Xd
+        agg = X_host.numel() * 8 * world / (float(cms.item()) * 1e-3) / 1e9
+        res['h2d_ceiling'] = {'bare_pinned_copy_of_X_all_ranks_at_once_gb_per_s': agg, 'ms': float(cms.item()),
+                              'e2e_h2d_gb_per_s': h2d * world / (ms_step * 1e-3) / 1e9,
+                              'e2e_fraction_of_bare_copy_time': float(cms.item()) / ms_step}
+    return res
 
 
 if __name__ == '__main__':

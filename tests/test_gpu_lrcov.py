@@ -93,3 +93,35 @@ def test_lr_cov_without_factorisation(vt, golden):
     J = rng.normal(size=(7, dim))
     lr = vt.LinearResponseCovariances(lambda par: par.sum(), np.zeros(dim), hessian_at_opt=H, factorize_hessian=False)
     assert_close(lr.get_lr_covariance_from_jacobians(J, J), J @ np.linalg.solve(H, J.T), rtol=1e-8, atol_scale=1e-10)
+
+
+def test_lr_cov_config4_full_size_vs_scipy(vt):
+    """BASELINE config 4 at its full size: mean-field normal VB of an MVN target with D = 4096 parameters
+    (2048 means + 2048 variances, closed-form Hessian), LR covariance of 2048 linear moments.  The dense Cholesky
+    factorisation and the 2048-column solve run through the blocked kernels (32 block columns; 256-row steps with
+    inverted diagonal blocks in the solve); parity against scipy's cho_factor / cho_solve - what the reference
+    runs (``solver_lib.py:27,29``; ``lr_cov_lib.py:106,172``) - at rtol 1e-8."""
+    import scipy.linalg
+    from oracle import models
+    dim, k = 2048, 2048
+    rng = np.random.RandomState(4)
+    a = rng.normal(size=(dim, dim + 16))
+    true_cov = a @ a.T / dim + np.eye(dim)
+    true_info = np.linalg.inv(true_cov)
+    true_mean = rng.normal(size=dim)
+    opt, H = models.mvn_kl_closed_form(true_mean, true_info)
+    assert H.shape == (4096, 4096)
+    J = rng.normal(size=(k, 2 * dim))
+    lr = vt.LinearResponseCovariances(lambda par: par.sum(), opt, hessian_at_opt=H)
+    cov = lr.get_lr_covariance_from_jacobians(J, J)
+    chol = scipy.linalg.cho_factor(H)
+    ref = J @ scipy.linalg.cho_solve(chol, J.T)
+    assert_close(cov, ref, rtol=1e-8, atol_scale=1e-11, what='config 4 LR covariance, D = 4096')
+    # the solver pieces on their own: factor, 2048-column solve, and a ragged dimension crossing the 256-blocks
+    solve = vt.solver_lib.get_cholesky_solver(H)
+    assert_close(solve(J.T), scipy.linalg.cho_solve(chol, J.T), rtol=1e-8, atol_scale=1e-11, what='potrs 2048 rhs')
+    for d2 in (4096 - 131, 300, 257, 129):
+        H2 = H[:d2, :d2]
+        B2 = J[:37, :d2].T
+        assert_close(vt.solver_lib.get_cholesky_solver(H2)(B2), scipy.linalg.cho_solve(scipy.linalg.cho_factor(H2), B2),
+                     rtol=1e-8, atol_scale=1e-11, what='potrs D = {}'.format(d2))

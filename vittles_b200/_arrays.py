@@ -29,12 +29,31 @@ def kind_of(a):
     return 'numpy'
 
 
+PINNED_STAGING_MIN_BYTES = 64 << 20
+
+
+def to_host(t):
+    """CPU copy of a device tensor.  Large results (the (D, N) sensitivity matrix is 82 GB at N = 1e7) go through a
+    PINNED buffer with one asynchronous copy - pageable memory moves at a fraction of the PCIe rate; the buffer comes
+    from torch's caching host allocator, so repeated calls reuse it."""
+    if not t.is_cuda:
+        return t
+    t = t.detach()
+    if t.numel() * t.element_size() < PINNED_STAGING_MIN_BYTES:
+        return t.cpu()
+    src = t if t.is_contiguous() else t.contiguous()
+    out = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+    out.copy_(src, non_blocking=True)
+    torch.cuda.current_stream(src.device).synchronize()
+    return out
+
+
 def as_kind(t, kind):
     if kind == 'cuda':
         return t
     if kind == 'cpu':
-        return t.cpu()
-    return t.detach().cpu().numpy()
+        return to_host(t)
+    return to_host(t).numpy()
 
 
 def like(t, proto):

@@ -46,8 +46,9 @@ class CudaBlockKernels:
 
     @staticmethod
     def gram(Z2):
-        """Z^T Z on the FP64 tensor-core engine."""
-        return ops.syrk_weighted(Z2, precision='f64')
+        """Z^T Z on the tensor cores: the FP64 DMMA engine, or for large Z the FP64-grade INT8 slicing engine
+        ('auto', same parity bar)."""
+        return ops.syrk_weighted(Z2, precision='auto')
 
     @staticmethod
     def dense_factor(S):

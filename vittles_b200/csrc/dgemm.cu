@@ -335,8 +335,16 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmParams p) 
 
 template <int AMODE, int BMODE, bool KSCALE, bool VEC, class CFG>
 int launch_cfg(const GemmParams& p, int grid, cudaStream_t stream) {
-  VT_CUDA(cudaFuncSetAttribute(dgemm_kernel<AMODE, BMODE, KSCALE, VEC, CFG>,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::SMEM_BYTES));
+  // once per instantiation and device: the attribute call costs as much host time as the launch itself, and the
+  // blocked Cholesky / triangular solves issue ~100 short GEMMs back to back
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  VT_CUDA(cudaGetDevice(&dev));
+  if (configured_dev != dev) {
+    VT_CUDA(cudaFuncSetAttribute(dgemm_kernel<AMODE, BMODE, KSCALE, VEC, CFG>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::SMEM_BYTES));
+    configured_dev = dev;
+  }
   dgemm_kernel<AMODE, BMODE, KSCALE, VEC, CFG><<<grid, CFG::NTHREADS, CFG::SMEM_BYTES, stream>>>(p);
   VT_LAUNCH_CHECK();
   return VT_OK;

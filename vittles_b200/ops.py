@@ -209,7 +209,7 @@ PRECISIONS = {'auto': 0, 'f64': 0, 'tf32': 1, 'tf32x3': 3, 'f64_ozaki': 0}
 # passes and fill its 128 x 64 tiles (N D^2 >= 1e11, e.g. N >= 1e5 at D = 1024), the FP64 DMMA engine otherwise
 # (and whenever the weights of the Hessian are not all non-negative: the slicing engine factors out sqrt(s)).
 AUTO_OZAKI_MIN_WORK = 1e11
-AUTO_OZAKI_MIN_DIM = 128
+AUTO_OZAKI_MIN_DIM = 512          # narrower outputs cover too few 128 x 64 tiles (measured at D = 320: no faster than DMMA)
 
 
 def _split(precision):

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     assert isinstance(lib.vt_last_error(), bytes)
     # inverted 128-blocks + scratch panel + flags + inverted 256-blocks
     assert lib.vt_potrf_dinv_doubles(1024) == 8 * 128 * 128 + 1024 * 128 + 10 + 4 * 256 * 256
-    assert lib.vt_potrf_dinv_doubles(130) == 2 * 128 * 128 + 130 * 128 + 4
+    assert lib.vt_potrf_dinv_doubles(130) == 2 * 128 * 128 + 130 * 128 + 4 + 1 * 256 * 256
 
 
 def test_no_cpu_fallback():

@@ -24,6 +24,14 @@ import sys
 import threading
 import time
 
+if '--impl' in sys.argv and 'reference' in sys.argv:
+    # The CPU arm uses every host core.  torch.distributed.run exports OMP_NUM_THREADS=1 to its workers and the BLAS
+    # pools of numpy and scipy size themselves from the environment when they are first loaded - so set it before
+    # either is imported (use_all_host_cores() additionally resizes the pools that are already there).
+    _n = str(len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1))
+    for _k in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ[_k] = _n
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -93,6 +101,7 @@ def use_all_host_cores():
         os.sched_setaffinity(0, ORIG_AFFINITY)      # undo the NUMA binding of the GPU legs
     ncores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
     try:
+        import scipy.linalg                         # noqa: F401  (load scipy's own BLAS before resizing the pools)
         from threadpoolctl import threadpool_limits, threadpool_info
         threadpool_limits(limits=ncores)           # stays in force for the life of the process
         return max([p.get('num_threads', 1) for p in threadpool_info()] + [1])

@@ -187,6 +187,38 @@ def test_quadratic_model_vs_golden(vt, golden, key):
                 assert_close(sens.predict_opt_par_from_hyper_par(lam0 + 0.001), g[key + '_pred'], rtol=1e-9)
 
 
+@pytest.mark.parametrize('key', ['t0l0', 't0l1', 't1l0', 't1l1'])
+def test_quadratic_model_through_patterns_vs_golden(vt, golden, key):
+    """The reference's QuadraticModel test set-up (``tests/test_utils.py:23-75``: NumericArrayPattern(lb=-20) +
+    FlattenFunctionInput) written with ``vittles_b200.patterns`` instead of paragami, through
+    HyperparameterSensitivityLinearApproximation on the GPU, against the golden values the unmodified reference
+    produced for the same four free / not-free combinations (``tests/test_sensitivity_lib.py:454-613``)."""
+    pg = vt.patterns
+    g = golden('linear_quadratic')
+    dim = 3
+    theta_free, lambda_free = key[1] == '1', key[3] == '1'
+    theta_pattern = pg.NumericArrayPattern(shape=(dim,), lb=-20.0)
+    lambda_pattern = pg.NumericArrayPattern(shape=(dim,), lb=-20.0)
+    vec = np.linspace(0.1, 0.3, num=dim)
+    matrix = np.outer(vec, vec) + np.eye(dim)
+
+    def get_objective(theta, lam):
+        A = torch.as_tensor(matrix, device=theta.device)
+        return 0.5 * theta @ A @ theta + lam @ theta
+    objective = pg.FlattenFunctionInput(get_objective, free=[theta_free, lambda_free], argnums=[0, 1],
+                                        patterns=[theta_pattern, lambda_pattern])
+    lam0_folded = np.linspace(0.5, 10.0, num=dim)
+    theta0_folded = -1 * np.linalg.solve(matrix, lam0_folded)
+    theta0 = theta_pattern.flatten(theta0_folded, theta_free)
+    lam0 = lambda_pattern.flatten(lam0_folded, lambda_free)
+    assert_close(theta0, g[key + '_theta0'], rtol=1e-13)
+    assert_close(lam0, g[key + '_lam0'], rtol=1e-13)
+    sens = vt.HyperparameterSensitivityLinearApproximation(objective, theta0, lam0, validate_optimum=True)
+    assert_close(sens.get_hessian_at_opt(), g[key + '_hess'], rtol=1e-9, atol_scale=1e-12)
+    assert_close(sens.get_dopt_dhyper(), g[key + '_sens'], rtol=1e-8, atol_scale=1e-11)
+    assert_close(sens.predict_opt_par_from_hyper_par(lam0 + 0.001), g[key + '_pred'], rtol=1e-9)
+
+
 def test_streamed_host_input_matches_resident(vt):
     """Pinned host X goes through the chunked-copy path (copies overlapped with
     the statistics + Hessian sweep); results must equal the resident path."""

@@ -14,5 +14,6 @@ from . import solver_lib
 from . import bivariate_sensitivity_lib
 from . import objectives
 from . import ops
+from . import patterns
 
 __version__ = '0.1.0'

@@ -318,8 +318,9 @@ def main():
         torch.cuda.synchronize()
         return a.elapsed_time(b) / reps, out
     reps = max(2, min(args.steps, 3))
-    t_stats, st = timed(lambda: obj.vt_stats(theta, w), reps)
-    t_syrk, H = timed(lambda: ops.syrk_weighted(X, st['s'], precision=engine), reps)
+    t_stats, st = timed(lambda: obj.vt_stats(theta, w, for_hessian=True), reps)     # as the step runs it: on the INT8
+    # engine the statistics pass also produces the per-feature scales of the Hessian assembly
+    t_syrk, H = timed(lambda: ops.syrk_weighted(X, st['s'], precision=engine, colmax=st.get('colmax')), reps)
     if world > 1:
         dist.all_reduce(H)
     t_chol, hinv = timed(lambda: ops.potrf(H).inverse(), reps)

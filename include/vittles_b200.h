@@ -100,6 +100,12 @@ size_t vt_glm_workspace_bytes(int D);
 int vt_glm_stats(const double* X, int64_t ldx, int64_t N, int D, const double* theta, const double* y,
                  const double* w, int family, double* z, double* resid, double* s, double* grad, double l2,
                  void* workspace, size_t workspace_bytes, void* stream);
+/* vt_glm_stats that also writes sq[n] = sqrt(s_n) and colmax[c] = the bit pattern of max_n sq_n |x_nc| (D <= 2048;
+ * workspace of 2 x vt_glm_workspace_bytes): the per-feature scales of the INT8 Hessian assembly (vt_syrk_ozaki)
+ * come out of the statistics pass instead of a sweep of their own. */
+int vt_glm_stats_colmax(const double* X, int64_t ldx, int64_t N, int D, const double* theta, const double* y,
+                        const double* w, int family, double* z, double* resid, double* s, double* grad, double l2,
+                        double* sq, uint64_t* colmax, void* workspace, size_t workspace_bytes, void* stream);
 /* q <= 4 Hessian-vector products in ONE pass over X: out (q x D) = V X^T diag(s) X + ridge V, V (q x D)
  * row-major - the shared mat_times_vec of a multi-right-hand-side CG (D <= 2048 for q > 1). */
 size_t vt_glm_hvp_multi_workspace_bytes(int D, int q);
@@ -179,10 +185,13 @@ int vt_ozaki_gemm(int M, int N, int K, const int8_t* A, int64_t lda, int64_t a_s
 /* vt_syrk_ozaki is vt_syrk_weighted (s >= 0) on the same engine: the contraction runs over the
  * observations, so the digits of sqrt(s_n) x_ni are written transposed with one power-of-two
  * scale per feature and per chunk of observations, and the chunks' lower-triangular Gram tiles
- * (split-K parts of <= 16384 observations: the INT32 bound) are accumulated in FP64.            */
+ * (split-K parts of <= 16384 observations: the INT32 bound) are accumulated in FP64.
+ * sq / colmax (both NULL, or both given): sqrt(s_n) and the column maxima of sqrt(s_n) |x_ni| as
+ * written by vt_glm_stats_colmax - the sweep over X that would compute them is then skipped.   */
 size_t vt_syrk_ozaki_workspace_bytes(int64_t N, int D, int nslices);
 int vt_syrk_ozaki(const double* X, int64_t ldx, int64_t N, int D, const double* s, double l2, double* H, int64_t ldh,
-                  int nslices, void* workspace, size_t workspace_bytes, void* stream);
+                  int nslices, const double* sq, const uint64_t* colmax, void* workspace, size_t workspace_bytes,
+                  void* stream);
 size_t vt_ij_apply_ozaki_workspace_bytes(int64_t N, int D, int nslices);
 int vt_ij_apply_ozaki(const double* Hinv, int64_t ldh, const double* X, int64_t ldx, int64_t N, int D,
                       const double* resid, double* S, int64_t lds, int nslices, void* workspace,

@@ -151,6 +151,35 @@ def test_hessian_assembly_on_the_int8_engine(vt, shape):
         vt.ops.syrk_weighted(X, -s - 1.0, precision='f64_ozaki')
 
 
+@pytest.mark.parametrize('shape', [(50000, 1024), (3001, 77), (40000, 2048)])
+def test_statistics_pass_hands_the_hessian_its_column_scales(vt, shape):
+    """vt_glm_stats_colmax: sqrt(s) and the per-feature maxima of sqrt(s_n) |x_ni| from the statistics pass are
+    bit-identical to what the INT8 Hessian assembly computes in its own sweep, so the Hessian is bit-identical too;
+    a NaN in X poisons exactly its column."""
+    N, D = shape
+    X = vt.ops.synth_design(23, 0, N, D, 'cuda')
+    theta = 0.3 * vt.ops.synth_theta(23, D, 'cuda')
+    y = (torch.rand(N, device='cuda', dtype=torch.float64) < 0.5).double()
+    w = torch.rand(N, device='cuda', dtype=torch.float64) + 0.5
+    z, resid, s, grad = vt.ops.glm_stats(X, theta, y, w)
+    z2, resid2, s2, grad2, (sq, cmax) = vt.ops.glm_stats(X, theta, y, w, want_colmax=True)
+    assert torch.equal(z, z2) and torch.equal(resid, resid2) and torch.equal(s, s2) and torch.equal(grad, grad2)
+    assert torch.equal(sq, torch.sqrt(s))
+    ref = (X.abs() * torch.sqrt(s)[:, None]).max(dim=0).values
+    assert torch.equal(cmax.view(torch.float64), ref)
+    H_own = vt.ops.syrk_weighted(X, s, precision='f64_ozaki')
+    H_fused = vt.ops.syrk_weighted(X, s, precision='f64_ozaki', colmax=(sq, cmax))
+    assert torch.equal(H_own, H_fused)
+    X[5, 3] = float('nan')
+    _, _, s3, _, (sq3, cmax3) = vt.ops.glm_stats(X, theta, y, w, want_colmax=True)
+    bad = torch.isnan(cmax3.view(torch.float64))
+    # row 5's z is NaN, so its s and sqrt(s) are NaN: every column with a non-zero entry in that row is poisoned -
+    # as in the engine's own sweep
+    H3 = vt.ops.syrk_weighted(X, s3, precision='f64_ozaki', colmax=(sq3, cmax3))
+    H3_own = vt.ops.syrk_weighted(X, s3, precision='f64_ozaki')
+    assert bool(bad.any()) and torch.equal(torch.isnan(H3), torch.isnan(H3_own))
+
+
 def test_ij_sensitivities_through_the_api_match_the_oracle(vt):
     """precision='f64_ozaki' through HyperparameterSensitivityLinearApproximation: the
     same rtol 1e-8 bar against the oracle as the default FP64 path."""

@@ -35,6 +35,7 @@ SIGNATURES = {
     'vt_syrk_weighted': (_I, [_P, _I64, _I64, _I, _P, _D, _P, _I64, _P, _SZ, _P]),
     'vt_glm_workspace_bytes': (_SZ, [_I]),
     'vt_glm_stats': (_I, [_P, _I64, _I64, _I, _P, _P, _P, _I, _P, _P, _P, _P, _D, _P, _SZ, _P]),
+    'vt_glm_stats_colmax': (_I, [_P, _I64, _I64, _I, _P, _P, _P, _I, _P, _P, _P, _P, _D, _P, _P, _P, _SZ, _P]),
     'vt_glm_hvp_multi_workspace_bytes': (_SZ, [_I, _I]),
     'vt_glm_hvp_multi': (_I, [_P, _I64, _I64, _I, _P, _P, _I, _D, _P, _P, _SZ, _P]),
     'vt_glm_hvp': (_I, [_P, _I64, _I64, _I, _P, _P, _D, _P, _P, _SZ, _P]),
@@ -54,7 +55,7 @@ SIGNATURES = {
     'vt_ozaki_slice': (_I, [_P, _I64, _I64, _I, _P, _I64, _I64, _I, _P, _P, _P]),
     'vt_ozaki_gemm': (_I, [_I, _I, _I, _P, _I64, _I64, _P, _I64, _I64, _I, _D, _P, _P, _P, _I64, _P]),
     'vt_syrk_ozaki_workspace_bytes': (_SZ, [_I64, _I, _I]),
-    'vt_syrk_ozaki': (_I, [_P, _I64, _I64, _I, _P, _D, _P, _I64, _I, _P, _SZ, _P]),
+    'vt_syrk_ozaki': (_I, [_P, _I64, _I64, _I, _P, _D, _P, _I64, _I, _P, _P, _P, _SZ, _P]),
     'vt_ij_apply_ozaki_workspace_bytes': (_SZ, [_I64, _I, _I]),
     'vt_ij_apply_ozaki': (_I, [_P, _I64, _P, _I64, _I64, _I, _P, _P, _I64, _I, _P, _SZ, _P]),
     'vt_gemv_workspace_bytes': (_SZ, [_I, _I64]),

@@ -150,8 +150,16 @@ size_t vt_glm_workspace_bytes(int D) { return glm_workspace_bytes(D); }
 int vt_glm_stats(const double* X, int64_t ldx, int64_t N, int D, const double* theta, const double* y,
                  const double* w, int family, double* z, double* resid, double* s, double* grad, double l2,
                  void* workspace, size_t workspace_bytes, void* stream) {
-  return glm_stats(X, ldx, N, D, theta, y, w, family, z, resid, s, grad, l2, static_cast<double*>(workspace),
-                   workspace_bytes, S(stream));
+  return glm_stats(X, ldx, N, D, theta, y, w, family, z, resid, s, grad, l2, nullptr, nullptr,
+                   static_cast<double*>(workspace), workspace_bytes, S(stream));
+}
+int vt_glm_stats_colmax(const double* X, int64_t ldx, int64_t N, int D, const double* theta, const double* y,
+                        const double* w, int family, double* z, double* resid, double* s, double* grad, double l2,
+                        double* sq, uint64_t* colmax, void* workspace, size_t workspace_bytes, void* stream) {
+  VT_REQUIRE(sq && colmax, "glm_stats_colmax: sq and colmax are required");
+  return glm_stats(X, ldx, N, D, theta, y, w, family, z, resid, s, grad, l2, sq,
+                   reinterpret_cast<unsigned long long*>(colmax), static_cast<double*>(workspace), workspace_bytes,
+                   S(stream));
 }
 
 size_t vt_glm_hvp_multi_workspace_bytes(int D, int q) { return glm_hvp_multi_workspace_bytes(D, q); }
@@ -268,8 +276,10 @@ int vt_ij_apply_ozaki(const double* Hinv, int64_t ldh, const double* X, int64_t 
 size_t vt_syrk_ozaki_workspace_bytes(int64_t N, int D, int nslices) { return syrk_ozaki_workspace_bytes(N, D, nslices); }
 
 int vt_syrk_ozaki(const double* X, int64_t ldx, int64_t N, int D, const double* s, double l2, double* H, int64_t ldh,
-                  int nslices, void* workspace, size_t workspace_bytes, void* stream) {
-  int st = syrk_ozaki(X, ldx, N, D, s, H, ldh, nslices, workspace, workspace_bytes, S(stream));
+                  int nslices, const double* sq, const uint64_t* colmax, void* workspace, size_t workspace_bytes,
+                  void* stream) {
+  int st = syrk_ozaki(X, ldx, N, D, s, H, ldh, nslices, sq, reinterpret_cast<const unsigned long long*>(colmax),
+                      workspace, workspace_bytes, S(stream));
   if (st != VT_OK) return st;
   if (l2 != 0.0) {
     add_diag_kernel<<<(D + 255) / 256, 256, 0, S(stream)>>>(H, ldh, D, l2);

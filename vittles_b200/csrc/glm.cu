@@ -79,9 +79,10 @@ struct StatsOp {
   const double* y; const double* w;
   double* z; double* resid; double* s;
   int family;
+  double* sq;        // CMAX kernels: sqrt(s_n), kept for the slicing kernels of the INT8 Hessian assembly
   struct Aux { double y, w; };
   __device__ Aux load(long n) const { return Aux{y[n], w ? w[n] : 1.0}; }
-  __device__ double operator()(long n, const double* t, const Aux& a) const {
+  __device__ double eval(long n, const double* t, const Aux& a, double* s_out) const {
     const double zz = t[0];
     double mu, var;
     if (family == GLM_LOGISTIC) { mu = sigmoid(zz); var = mu * (1.0 - mu); }
@@ -90,10 +91,38 @@ struct StatsOp {
     const double r = mu - a.y;
     if (z) z[n] = zz;
     if (resid) resid[n] = r;
-    if (s) s[n] = a.w * var;
+    const double sv = a.w * var;
+    if (s) s[n] = sv;
+    *s_out = sv;
     return a.w * r;
   }
+  __device__ double operator()(long n, const double* t, const Aux& a) const {
+    double sv;
+    return eval(n, t, a, &sv);
+  }
+  // uq[0] = w_n resid_n (the gradient weight), uq[1] = sqrt(s_n) (the weight of the column maxima)
+  __device__ void stats2(long n, const double* t, const Aux& a, double* uq) const {
+    double sv;
+    uq[0] = eval(n, t, a, &sv);
+    const double q = (sv == sv) ? sqrt(fmax(sv, 0.0)) : sv;        // a NaN weight stays NaN (fmax would drop it)
+    if (sq) sq[n] = q;
+    uq[1] = q;
+  }
 };
+
+// colmax[c] = max over the CTAs, as the bit pattern of a non-negative double (orders like an unsigned integer; the
+// quiet-NaN pattern is above every finite one) - the form the slicing kernels read
+__global__ void xtfx_reduce_max_kernel(const double* partial_max, int ncta, int stride, int D,
+                                       unsigned long long* colmax) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  unsigned long long m = 0ULL;
+  for (int k = 0; k < ncta; ++k) {
+    const unsigned long long v = (unsigned long long)__double_as_longlong(partial_max[(size_t)k * stride + c]);
+    m = v > m ? v : m;
+  }
+  colmax[c] = m;
+}
 
 struct HvpOp {
   const double* s;
@@ -135,16 +164,16 @@ struct DirDerivOp {
   }
 };
 
-template <class RowOp, int Q, int CPT, int NOUT = 1>
+template <class RowOp, int Q, int CPT, int NOUT = 1, bool CMAX = false>
 int launch_xtfx(const XtfxParams& p, const RowOp& op, cudaStream_t stream, int* grid_out) {
   constexpr int R = (CPT <= 8) ? 8 / CPT : 1;
   constexpr int CTAS_PER_SM = (R * CPT <= 8 && NOUT == 1) ? 2 : 1;
   const size_t smem = xtfx_smem_bytes(p.Dp, R, Q);
-  VT_CUDA(cudaFuncSetAttribute(xtfx_kernel<RowOp, Q, CPT, R, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VT_CUDA(cudaFuncSetAttribute(xtfx_kernel<RowOp, Q, CPT, R, NOUT, CMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long nblocks = (p.N + R - 1) / R;
   const long cap = (long)num_sms() * CTAS_PER_SM;
   const int grid = (int)(nblocks < cap ? nblocks : cap);
-  xtfx_kernel<RowOp, Q, CPT, R, NOUT><<<grid, XT_THREADS, smem, stream>>>(p, op);
+  xtfx_kernel<RowOp, Q, CPT, R, NOUT, CMAX><<<grid, XT_THREADS, smem, stream>>>(p, op);
   VT_LAUNCH_CHECK();
   *grid_out = grid;
   return VT_OK;
@@ -164,6 +193,16 @@ int dispatch_cpt(const XtfxParams& p, const RowOp& op, cudaStream_t stream, int*
   return VT_ERR_INVALID;
 }
 
+// statistics pass that also produces the column maxima (D <= 2048: the accumulators double)
+int dispatch_stats_cmax(const XtfxParams& p, const StatsOp& op, cudaStream_t stream, int* grid_out) {
+  const int D = p.D;
+  if (D <= 512) return launch_xtfx<StatsOp, 1, 1, 1, true>(p, op, stream, grid_out);
+  if (D <= 1024) return launch_xtfx<StatsOp, 1, 2, 1, true>(p, op, stream, grid_out);
+  if (D <= 2048) return launch_xtfx<StatsOp, 1, 4, 1, true>(p, op, stream, grid_out);
+  set_error("glm_stats: column maxima are fused for D <= 2048 only (D = %d)", D);
+  return VT_ERR_INVALID;
+}
+
 int make_params(XtfxParams& p, const double* X, long ldx, long N, int D, const double* V, double* workspace,
                 size_t workspace_bytes, bool need_partial) {
   VT_REQUIRE(X && V, "xtfx: null pointer");
@@ -173,6 +212,7 @@ int make_params(XtfxParams& p, const double* X, long ldx, long N, int D, const d
   p.contiguous = (ldx == D);
   p.bulk = (D % 2 == 0) && (reinterpret_cast<uintptr_t>(X) % 16 == 0) && (p.contiguous || ldx % 2 == 0);
   p.partial = nullptr;
+  p.partial_max = nullptr;
   if (need_partial) {
     VT_REQUIRE(workspace && workspace_bytes >= glm_workspace_bytes(D),
                "xtfx: workspace too small: need %zu bytes", glm_workspace_bytes(D));
@@ -186,19 +226,31 @@ int make_params(XtfxParams& p, const double* X, long ldx, long N, int D, const d
 size_t glm_workspace_bytes(int D) { return (size_t)num_sms() * 2 * ((D + 1) & ~1) * 8; }
 
 int glm_stats(const double* X, long ldx, long N, int D, const double* theta, const double* y, const double* w,
-              int family, double* z, double* resid, double* s, double* grad, double l2, double* workspace,
-              size_t workspace_bytes, cudaStream_t stream) {
+              int family, double* z, double* resid, double* s, double* grad, double l2, double* sq,
+              unsigned long long* colmax, double* workspace, size_t workspace_bytes, cudaStream_t stream) {
   VT_REQUIRE(y, "glm_stats: y is null");
   VT_REQUIRE(family >= 0 && family <= 2, "glm_stats: unknown family %d", family);
+  const bool cmax = colmax != nullptr;
+  VT_REQUIRE(!cmax || (sq && D <= 2048), "glm_stats: fused column maxima need `sq` and D <= 2048");
   XtfxParams p;
-  int st = make_params(p, X, ldx, N, D, theta, workspace, workspace_bytes, grad != nullptr);
+  int st = make_params(p, X, ldx, N, D, theta, workspace, workspace_bytes, grad != nullptr || cmax);
   if (st != VT_OK) return st;
-  StatsOp op{y, w, z, resid, s, family};
+  StatsOp op{y, w, z, resid, s, family, cmax ? sq : nullptr};
   int grid = 0;
-  st = dispatch_cpt<StatsOp, 1>(p, op, stream, &grid);
+  if (cmax) {
+    VT_REQUIRE(workspace_bytes >= 2 * glm_workspace_bytes(D), "glm_stats: workspace too small for the column maxima");
+    p.partial_max = workspace + glm_workspace_bytes(D) / 8;
+    st = dispatch_stats_cmax(p, op, stream, &grid);
+  } else {
+    st = dispatch_cpt<StatsOp, 1>(p, op, stream, &grid);
+  }
   if (st != VT_OK) return st;
   if (grad) {
     xtfx_reduce_kernel<<<(D + 255) / 256, 256, 0, stream>>>(p.partial, grid, p.Dp, D, grad, 1.0, theta, l2);
+    VT_LAUNCH_CHECK();
+  }
+  if (cmax) {
+    xtfx_reduce_max_kernel<<<(D + 255) / 256, 256, 0, stream>>>(p.partial_max, grid, p.Dp, D, colmax);
     VT_LAUNCH_CHECK();
   }
   return VT_OK;

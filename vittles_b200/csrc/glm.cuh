@@ -10,10 +10,11 @@ constexpr int GLM_MAX_BDERIV = 8;   // highest derivative order of b(z) supporte
 size_t glm_workspace_bytes(int D);
 
 // z = X theta; resid = b'(z) - y; s = w b''(z); grad = X^T (w resid) + l2 theta.
-// Any of z/resid/s/grad may be null.
+// Any of z/resid/s/grad may be null.  colmax != null (D <= 2048, workspace 2 x glm_workspace_bytes): the same pass
+// also writes sq[n] = sqrt(s_n) and colmax[c] = bit pattern of max_n sq_n |x_nc| - the inputs of syrk_ozaki.
 int glm_stats(const double* X, long ldx, long N, int D, const double* theta, const double* y, const double* w,
-              int family, double* z, double* resid, double* s, double* grad, double l2, double* workspace,
-              size_t workspace_bytes, cudaStream_t stream);
+              int family, double* z, double* resid, double* s, double* grad, double l2, double* sq,
+              unsigned long long* colmax, double* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 // out = X^T (s .* (X v)) + ridge * v
 int glm_hvp(const double* X, long ldx, long N, int D, const double* s, const double* v, double ridge, double* out,

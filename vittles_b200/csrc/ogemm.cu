@@ -1056,7 +1056,8 @@ size_t syrk_ozaki_workspace_bytes(long N, int D, int nslices) {
 }
 
 int syrk_ozaki(const double* X, long ldx, long N, int D, const double* s, double* H, long ldh, int nslices,
-               void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+               const double* sq_in, const unsigned long long* colmax_in, void* workspace, size_t workspace_bytes,
+               cudaStream_t stream) {
   VT_REQUIRE(X && H && workspace, "syrk_ozaki: null pointer");
   VT_REQUIRE(D >= 1 && N >= 1 && ldx >= D && ldh >= D, "syrk_ozaki: bad shape");
   VT_REQUIRE(nslices >= OZAKI_MIN_SLICES && nslices <= OZAKI_MAX_SLICES, "syrk_ozaki: 5, 6 or 7 slices");
@@ -1076,10 +1077,17 @@ int syrk_ozaki(const double* X, long ldx, long N, int D, const double* s, double
   w += p.sq_bytes;
   double* P = reinterpret_cast<double*>(w);
   const long slice_stride = (long)D * p.ld;
-  // one sweep over all of X: sqrt of the weights and the per-feature maxima of sqrt(s_n) |x_ni| (the power-of-two
-  // scale of each row of X^T is common to all chunks: the error bound is relative to sigma_i sigma_j anyway)
-  VT_CUDA(cudaMemsetAsync(cmax, 0, (size_t)D * 8, stream));
-  {
+  // sqrt of the weights and the per-feature maxima of sqrt(s_n) |x_ni| (the power-of-two scale of each row of X^T
+  // is common to all chunks: the error bound is relative to sigma_i sigma_j anyway): taken from the caller when the
+  // statistics pass has already produced them (vt_glm_stats_colmax), else one sweep over all of X
+  VT_REQUIRE((sq_in == nullptr) == (colmax_in == nullptr), "syrk_ozaki: sq and colmax come together");
+  const double* sq_use = sq;
+  const unsigned long long* cmax_use = cmax;
+  if (colmax_in) {
+    sq_use = sq_in;
+    cmax_use = colmax_in;
+  } else {
+    VT_CUDA(cudaMemsetAsync(cmax, 0, (size_t)D * 8, stream));
     long nsteps = (N + 31) / 32;
     const long cap = (long)num_sms() * 8;
     ozaki_colmax_kernel<<<(unsigned)(nsteps < cap ? nsteps : cap), 256, 0, stream>>>(X, ldx, N, D, s, sq, cmax);
@@ -1106,9 +1114,9 @@ int syrk_ozaki(const double* X, long ldx, long N, int D, const double* s, double
     const long cap = (long)num_sms() * (overlap ? 1 : 6);
     const unsigned tgrid = (unsigned)(tiles < cap ? tiles : cap);
     switch (nslices) {
-      case 5: ozaki_slice_t_kernel<5><<<tgrid, 256, 0, slicer>>>(X + r0 * ldx, ldx, rows, D, sq + r0, cmax, Xs[b], p.ld, slice_stride, sigma); break;
-      case 6: ozaki_slice_t_kernel<6><<<tgrid, 256, 0, slicer>>>(X + r0 * ldx, ldx, rows, D, sq + r0, cmax, Xs[b], p.ld, slice_stride, sigma); break;
-      default: ozaki_slice_t_kernel<7><<<tgrid, 256, 0, slicer>>>(X + r0 * ldx, ldx, rows, D, sq + r0, cmax, Xs[b], p.ld, slice_stride, sigma); break;
+      case 5: ozaki_slice_t_kernel<5><<<tgrid, 256, 0, slicer>>>(X + r0 * ldx, ldx, rows, D, sq_use + r0, cmax_use, Xs[b], p.ld, slice_stride, sigma); break;
+      case 6: ozaki_slice_t_kernel<6><<<tgrid, 256, 0, slicer>>>(X + r0 * ldx, ldx, rows, D, sq_use + r0, cmax_use, Xs[b], p.ld, slice_stride, sigma); break;
+      default: ozaki_slice_t_kernel<7><<<tgrid, 256, 0, slicer>>>(X + r0 * ldx, ldx, rows, D, sq_use + r0, cmax_use, Xs[b], p.ld, slice_stride, sigma); break;
     }
     VT_LAUNCH_CHECK();
     if (overlap) {

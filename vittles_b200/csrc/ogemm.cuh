@@ -50,7 +50,10 @@ int ij_apply_ozaki(const double* Hinv, long ldh, const double* X, long ldx, long
 // feature, the lower tiles of the chunk's Gram matrix run as split-K parts of at most 16384
 // observations (INT32 bound) and are accumulated in FP64.
 size_t syrk_ozaki_workspace_bytes(long N, int D, int nslices);
+// sq_in / colmax_in (both or neither): sqrt(s_n) and the bit patterns of max_n sqrt(s_n) |x_ni| when the statistics
+// pass has produced them already (glm_stats with colmax) - the sweep over X that computes them is then skipped.
 int syrk_ozaki(const double* X, long ldx, long N, int D, const double* s, double* H, long ldh, int nslices,
-               void* workspace, size_t workspace_bytes, cudaStream_t stream);
+               const double* sq_in, const unsigned long long* colmax_in, void* workspace, size_t workspace_bytes,
+               cudaStream_t stream);
 
 }  // namespace vt

@@ -30,6 +30,7 @@ struct XtfxParams {
   const double* X; long ldx; long N; int D;
   const double* V;        // Q x D directions, row-major, contiguous
   double* partial;        // [grid][NOUT][Dp] column sums per CTA (null: skip the transposed pass)
+  double* partial_max;    // CMAX kernels: [grid][Dp] column maxima of q_n |x_nc| per CTA (q_n from op.stats2)
   int Dp;                 // D rounded up to even
   int bulk;               // 1: rows can be staged with cp.async.bulk
   int contiguous;         // 1: ldx == D, a block of rows is one contiguous copy
@@ -68,7 +69,7 @@ __device__ __forceinline__ void fence_barrier_init() {
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 inline size_t xtfx_smem_bytes(int Dp, int R, int Q) {
-  return (size_t)XT_NBUF * R * Dp * 8 + (size_t)(8 * R * Q + R * Q) * 8 + XT_NBUF * 8 + 128;
+  return (size_t)XT_NBUF * R * Dp * 8 + (size_t)(8 * R * Q + R * Q + R) * 8 + XT_NBUF * 8 + 128;
 }
 
 // R rows per block, CPT double2 columns per thread: R*CPT = 8 gives 32 KB blocks at
@@ -77,14 +78,21 @@ inline size_t xtfx_smem_bytes(int Dp, int R, int Q) {
 // CTA per SM left stats at 62% and the HVP at 79% of HBM peak, profiles/r01).
 // NOUT = 1: one output vector, u_n = op(n, t, aux).  NOUT = Q > 1: Q output vectors, op.multi(n, t, aux, u) fills
 // u_j - the accumulators of all Q outputs live in registers, so the CTA count per SM drops to one.
-template <class RowOp, int Q, int CPT, int R, int NOUT = 1>
+// CMAX: additionally keep max_n q_n |x_nc| per column, q_n the second value of op.stats2 (the column scales of the
+// INT8 slicing engine's Hessian assembly come out of the statistics pass instead of a sweep of their own); a
+// non-finite product poisons its column with NaN (fmax alone would drop it).
+__device__ __forceinline__ double xt_nanmax(double m, double v) {
+  return (v <= 1.7976931348623157e308 && m == m) ? fmax(m, v) : __longlong_as_double(0x7ff8000000000000LL);
+}
+template <class RowOp, int Q, int CPT, int R, int NOUT = 1, bool CMAX = false>
 __global__ void __launch_bounds__(XT_THREADS, (R * CPT <= 8 && NOUT == 1) ? 2 : 1) xtfx_kernel(const XtfxParams p, const RowOp op) {
   extern __shared__ __align__(128) unsigned char xt_raw[];
   const int Dp = p.Dp;
   double* bufs = reinterpret_cast<double*>(xt_raw);
   double* s_part = bufs + (size_t)XT_NBUF * R * Dp;   // [8][R][Q]
   double* s_u = s_part + 8 * R * Q;                    // [R][NOUT]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_u + R * Q);
+  double* s_q = s_u + R * Q;                           // [R] (CMAX)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_q + R);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long nblocks = (p.N + R - 1) / R;
@@ -126,6 +134,9 @@ __global__ void __launch_bounds__(XT_THREADS, (R * CPT <= 8 && NOUT == 1) ? 2 : 
   for (int o = 0; o < NOUT; ++o)
 #pragma unroll
     for (int i = 0; i < CPT; ++i) acc[o][i] = make_double2(0.0, 0.0);
+  double2 cmx[CMAX ? CPT : 1];
+#pragma unroll
+  for (int i = 0; i < (CMAX ? CPT : 1); ++i) cmx[i] = make_double2(0.0, 0.0);
 
   if (p.bulk && tid == 0) {
     for (int s = 0; s < XT_NBUF; ++s) {
@@ -191,7 +202,12 @@ __global__ void __launch_bounds__(XT_THREADS, (R * CPT <= 8 && NOUT == 1) ? 2 : 
         for (int w = 0; w < 8; ++w) s += s_part[(w * R + tid) * Q + j];
         t[j] = s;
       }
-      if constexpr (NOUT == 1) {
+      if constexpr (CMAX) {
+        double uq[2] = {0.0, 0.0};
+        if (tid < rows) op.stats2(row0 + tid, t, aux, uq);
+        s_u[tid] = uq[0];
+        s_q[tid] = uq[1];
+      } else if constexpr (NOUT == 1) {
         s_u[tid] = (tid < rows) ? op(row0 + tid, t, aux) : 0.0;
       } else {
         double u[NOUT];
@@ -216,6 +232,17 @@ __global__ void __launch_bounds__(XT_THREADS, (R * CPT <= 8 && NOUT == 1) ? 2 : 
             acc[o][i].y = fma(u, x[r][i].y, acc[o][i].y);
           }
         }
+      if constexpr (CMAX) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const double q = s_q[r];
+#pragma unroll
+          for (int i = 0; i < CPT; ++i) {
+            cmx[i].x = xt_nanmax(cmx[i].x, q * fabs(x[r][i].x));
+            cmx[i].y = xt_nanmax(cmx[i].y, q * fabs(x[r][i].y));
+          }
+        }
+      }
     }
     // s_part / s_u are rewritten only after the next block's first barrier
   }
@@ -227,6 +254,13 @@ __global__ void __launch_bounds__(XT_THREADS, (R * CPT <= 8 && NOUT == 1) ? 2 : 
         const int c = 2 * tid + 512 * i;
         if (c < Dp) *reinterpret_cast<double2*>(p.partial + ((size_t)blockIdx.x * NOUT + o) * Dp + c) = acc[o][i];
       }
+    if constexpr (CMAX) {
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) {
+        const int c = 2 * tid + 512 * i;
+        if (c < Dp) *reinterpret_cast<double2*>(p.partial_max + (size_t)blockIdx.x * Dp + c) = cmx[i];
+      }
+    }
   }
 }
 

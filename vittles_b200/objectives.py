@@ -134,7 +134,7 @@ class GLMObjective(StructuredObjective):
         """(stats, H) in one sweep.  While a host transfer is in flight the sweep
         runs chunk by chunk behind the copies; otherwise it is vt_stats + vt_hessian."""
         if self._host_src is None and not self._pending:
-            stats = self.vt_stats(theta, w)
+            stats = self.vt_stats(theta, w, for_hessian=True)
             return stats, self.vt_hessian(theta, w, stats)
         dev = self.X.device
         theta = to_device(theta, dev)
@@ -150,10 +150,13 @@ class GLMObjective(StructuredObjective):
         pending, self._pending = self._pending, []
         for r0, r1, ev in pending:
             cur.wait_event(ev)
-            _, _, _, g = ops.glm_stats(self.X[r0:r1], theta, self.y[r0:r1], None if w is None else w[r0:r1],
-                                       self.family, want_grad=True, out=(z[r0:r1], resid[r0:r1], s[r0:r1]))
-            grad += g
-            ops.syrk_weighted(self.X[r0:r1], s[r0:r1], out=Hc, precision=self.precision)
+            wc = None if w is None else w[r0:r1]
+            fused = self._wants_colmax(r1 - r0, wc)
+            st = ops.glm_stats(self.X[r0:r1], theta, self.y[r0:r1], wc, self.family, want_grad=True,
+                               out=(z[r0:r1], resid[r0:r1], s[r0:r1]), want_colmax=fused)
+            grad += st[3]
+            ops.syrk_weighted(self.X[r0:r1], s[r0:r1], out=Hc, precision='f64_ozaki' if fused else self.precision,
+                              colmax=st[4] if fused else None)
             H += Hc
         self._allreduce(grad)
         self._allreduce(H)
@@ -172,17 +175,30 @@ class GLMObjective(StructuredObjective):
         return val + 0.5 * self.l2 * torch.sum(theta * theta)
 
     # -- kernel hooks ---------------------------------------------------------
-    def vt_stats(self, theta, w=None, want_grad=True):
-        """z, resid = b'(z) - y, s = w b''(z) and the (all-reduced) gradient."""
+    def _wants_colmax(self, n_rows, w):
+        """True when the Hessian assembly of these rows will run on the INT8 slicing engine and the statistics pass
+        can hand it the per-feature scales (one sweep over X less)."""
+        d = self.X.shape[1]
+        return d <= ops.COLMAX_MAX_DIM and ops.resolve_precision(self.precision, n_rows, d, w) == 'f64_ozaki'
+
+    def vt_stats(self, theta, w=None, want_grad=True, for_hessian=False):
+        """z, resid = b'(z) - y, s = w b''(z) and the (all-reduced) gradient.  ``for_hessian``: the caller will
+        assemble the Hessian from these statistics - on the INT8 slicing engine the pass then also produces the
+        per-feature scales of that assembly (``colmax`` entry), sparing it a sweep over X."""
         self._wait_resident()
         theta = to_device(theta, self.X.device)
         w = None if w is None else to_device(w, self.X.device).contiguous()
-        z, resid, s, grad = ops.glm_stats(self.X, theta, self.y, w, self.family, l2=0.0, want_grad=want_grad)
+        fused = for_hessian and self._wants_colmax(self.X.shape[0], w)
+        st = ops.glm_stats(self.X, theta, self.y, w, self.family, l2=0.0, want_grad=want_grad, want_colmax=fused)
+        z, resid, s, grad = st[:4]
         if grad is not None:
             self._allreduce(grad)
             if self.l2 != 0.0:
                 grad = grad + self.l2 * theta
-        return dict(z=z, resid=resid, s=s, grad=grad)
+        out = dict(z=z, resid=resid, s=s, grad=grad)
+        if fused:
+            out['colmax'] = st[4]
+        return out
 
     def vt_grad(self, theta, w):
         return self.vt_stats(theta, w)['grad']
@@ -190,9 +206,11 @@ class GLMObjective(StructuredObjective):
     def vt_hessian(self, theta, w, stats=None):
         """H = X^T diag(w b''(z)) X + l2 I, all-reduced over the group."""
         if stats is None:
-            stats = self.vt_stats(theta, w, want_grad=False)
+            stats = self.vt_stats(theta, w, want_grad=False, for_hessian=True)
         self._wait_resident()
-        H = ops.syrk_weighted(self.X, stats['s'], l2=0.0, precision=self.precision)
+        cm = stats.get('colmax')
+        H = ops.syrk_weighted(self.X, stats['s'], l2=0.0, precision='f64_ozaki' if cm is not None else self.precision,
+                              colmax=cm)
         self._allreduce(H)
         if self.l2 != 0.0:
             H.diagonal().add_(self.l2)

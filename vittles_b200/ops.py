@@ -231,10 +231,12 @@ def resolve_precision(precision, N, D, weights=None):
     return 'f64_ozaki'
 
 
-def syrk_weighted(X, s=None, l2=0.0, out=None, precision='f64'):
+def syrk_weighted(X, s=None, l2=0.0, out=None, precision='f64', colmax=None):
     """H = X^T diag(s) X + l2 I  (FP64 DMMA, deterministic split-K; or, for
     s >= 0, the INT8 error-free-slicing engine 'f64_ozaki' (FP64-grade) or the
-    optional reduced-precision TF32 / TF32x3 tcgen05 path)."""
+    optional reduced-precision TF32 / TF32x3 tcgen05 path).  ``colmax=(sq, cmax)``
+    from ``glm_stats(..., want_colmax=True)`` spares the INT8 engine its own sweep
+    over X for the per-feature scales."""
     lib = _cabi.require_cuda()
     _mat(X, 'X')
     N, D = X.shape
@@ -253,8 +255,11 @@ def syrk_weighted(X, s=None, l2=0.0, out=None, precision='f64'):
                          "use precision='f64'".format(precision))
     if precision == 'f64_ozaki':
         ws, wsb = _ws('syrk_ozaki', lib.vt_syrk_ozaki_workspace_bytes(N, D, OZAKI_SLICES), X.device)
-        check(lib.vt_syrk_ozaki(ptr(X), _ld(X), N, D, ptr(s), float(l2), ptr(out), _ld(out), OZAKI_SLICES, ptr(ws), wsb,
-                                stream()))
+        sq, cmax = colmax if (colmax is not None and s is not None) else (None, None)
+        if sq is not None and (sq.numel() != N or cmax.numel() != D or cmax.dtype != torch.int64):
+            raise ValueError('colmax must be (sq (N,) float64, cmax (D,) int64) from glm_stats(want_colmax=True)')
+        check(lib.vt_syrk_ozaki(ptr(X), _ld(X), N, D, ptr(s), float(l2), ptr(out), _ld(out), OZAKI_SLICES, ptr(sq),
+                                ptr(cmax), ptr(ws), wsb, stream()))
         return out
     if split:
         ws, wsb = _ws('syrk_tf32', lib.vt_syrk_tf32_workspace_bytes(N, D, split), X.device)
@@ -268,10 +273,16 @@ def syrk_weighted(X, s=None, l2=0.0, out=None, precision='f64'):
 
 
 # ------------------------------------------------------------- GLM passes ----
-def glm_stats(X, theta, y, w=None, family='logistic', l2=0.0, want_grad=True, want_z=True, out=None):
+COLMAX_MAX_DIM = 2048         # the statistics pass can carry the column maxima up to this width
+
+
+def glm_stats(X, theta, y, w=None, family='logistic', l2=0.0, want_grad=True, want_z=True, out=None, want_colmax=False):
     """One pass over X: z = X theta, resid = b'(z) - y, s = w b''(z) and
     (optionally) grad = X^T (w resid) + l2 theta.  ``out=(z, resid, s)`` writes the
-    per-observation outputs into existing (slices of) tensors."""
+    per-observation outputs into existing (slices of) tensors.  ``want_colmax`` (D <= 2048):
+    the same pass also yields ``(sq, cmax)`` = sqrt(s) and the bit patterns of
+    max_n sqrt(s_n) |x_nc| - the per-feature scales ``syrk_weighted(precision='f64_ozaki')``
+    otherwise sweeps X for - returned as a fifth value."""
     lib = _cabi.require_cuda()
     _mat(X, 'X')
     N, D = X.shape
@@ -283,6 +294,16 @@ def glm_stats(X, theta, y, w=None, family='logistic', l2=0.0, want_grad=True, wa
         resid = torch.empty(N, dtype=torch.float64, device=dev)
         s = torch.empty(N, dtype=torch.float64, device=dev)
     grad = torch.empty(D, dtype=torch.float64, device=dev) if want_grad else None
+    if want_colmax:
+        if D > COLMAX_MAX_DIM:
+            raise ValueError('glm_stats: want_colmax needs D <= {}'.format(COLMAX_MAX_DIM))
+        sq = torch.empty(N, dtype=torch.float64, device=dev)
+        cmax = torch.empty(D, dtype=torch.int64, device=dev)
+        ws, wsb = _ws('glm', 2 * lib.vt_glm_workspace_bytes(D), dev)
+        check(lib.vt_glm_stats_colmax(ptr(X), _ld(X), N, D, ptr(_f64(theta, 'theta').contiguous()), ptr(_f64(y, 'y')),
+                                      ptr(_vec_opt(w, 'w', N)), _cabi.GLM_FAMILIES[family], ptr(z), ptr(resid), ptr(s),
+                                      ptr(grad), float(l2), ptr(sq), ptr(cmax), ptr(ws), wsb, stream()))
+        return z, resid, s, grad, (sq, cmax)
     ws, wsb = _ws('glm', lib.vt_glm_workspace_bytes(D), dev)
     check(lib.vt_glm_stats(ptr(X), _ld(X), N, D, ptr(_f64(theta, 'theta').contiguous()), ptr(_f64(y, 'y')),
                            ptr(_vec_opt(w, 'w', N)), _cabi.GLM_FAMILIES[family], ptr(z), ptr(resid), ptr(s), ptr(grad), float(l2),

@@ -237,8 +237,6 @@ def main():
     group = None
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        # keep stdout to the one JSON line: NCCL prints its version banner there at VERSION level
-        os.environ.setdefault('NCCL_DEBUG', 'WARN')
         dist.init_process_group('nccl', device_id=dev)
         group = dist.group.WORLD
 

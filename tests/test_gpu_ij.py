@@ -308,3 +308,21 @@ def test_default_engine_at_bench_width_vs_oracle(vt):
     obj64 = vt.objectives.GLMObjective(Xd, yd, family='logistic', precision='f64')
     sens64 = vt.HyperparameterSensitivityLinearApproximation(obj64, theta, wd)
     assert_close(sens64.get_dopt_dhyper(), S_ref, rtol=1e-8, atol_scale=1e-12, what='dopt_dhyper (f64 DMMA, D=1024)')
+
+
+def test_large_results_reach_the_host_through_pinned_staging(vt, monkeypatch):
+    """get_dopt_dhyper() on numpy / CPU inputs returns the (D, N) matrix on the host (``sensitivity_lib.py:230-231``):
+    large results go through one pinned buffer, or - when the host cannot pin that much - through two pinned
+    staging buffers into pageable memory.  Both paths are exercised here with small thresholds."""
+    from vittles_b200 import _arrays
+    g = torch.Generator(device='cuda').manual_seed(0)
+    t = torch.randn(37, 1001, device='cuda', dtype=torch.float64, generator=g)
+    ref = t.cpu()
+    monkeypatch.setattr(_arrays, 'PINNED_STAGING_MIN_BYTES', 1024)
+    out = _arrays.to_host(t)
+    assert not out.is_cuda and out.is_pinned() and torch.equal(out, ref)
+    assert torch.equal(_arrays.to_host(t.T), ref.T)                           # non-contiguous source
+    monkeypatch.setattr(_arrays, 'STAGING_BYTES', 8 * 5000)                   # 8 chunks, ragged tail
+    staged = _arrays._to_host_staged(t)
+    assert not staged.is_cuda and staged.shape == ref.shape and torch.equal(staged, ref)
+    assert isinstance(_arrays.as_kind(t, 'numpy'), np.ndarray)

@@ -42,10 +42,44 @@ def to_host(t):
     if t.numel() * t.element_size() < PINNED_STAGING_MIN_BYTES:
         return t.cpu()
     src = t if t.is_contiguous() else t.contiguous()
-    out = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+    try:
+        out = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+    except RuntimeError:
+        # the host cannot pin that much (the 82 GB result next to 82 GB of pinned inputs): pageable destination,
+        # filled through two pinned staging buffers - the CPU copy of chunk i-1 runs behind the transfer of chunk i
+        return _to_host_staged(src)
     out.copy_(src, non_blocking=True)
     torch.cuda.current_stream(src.device).synchronize()
     return out
+
+
+STAGING_BYTES = 512 << 20
+
+
+def _to_host_staged(src):
+    flat = src.reshape(-1)
+    n = flat.numel()
+    out = torch.empty(n, dtype=src.dtype)
+    per = max(1, STAGING_BYTES // src.element_size())
+    stage = [torch.empty(min(per, n), dtype=src.dtype, pin_memory=True) for _ in range(2)]
+    events = [torch.cuda.Event(), torch.cuda.Event()]
+    stream = torch.cuda.current_stream(src.device)
+    pending = None                                   # (offset, length, buffer index) of the chunk in flight
+    for i, off in enumerate(range(0, n, per)):
+        b = i & 1
+        ln = min(per, n - off)
+        stage[b][:ln].copy_(flat[off:off + ln], non_blocking=True)
+        events[b].record(stream)
+        if pending is not None:
+            po, pl, pb = pending
+            events[pb].synchronize()
+            out[po:po + pl].copy_(stage[pb][:pl])
+        pending = (off, ln, b)
+    if pending is not None:
+        po, pl, pb = pending
+        events[pb].synchronize()
+        out[po:po + pl].copy_(stage[pb][:pl])
+    return out.reshape(src.shape)
 
 
 def as_kind(t, kind):

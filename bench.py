@@ -326,6 +326,41 @@ def main():
     apply_tflops = 2.0 * D * D * n_loc / (t_apply * 1e-3) / 1e12
     syrk_tflops = float(D) * (D + 1) * n_loc / (t_syrk * 1e-3) / 1e12
     stats_gbs = 8.0 * D * n_loc / (t_stats * 1e-3) / 1e9
+    # the dominant kernel on its own, sustained: the GEMM of one pre-sliced chunk in a >= 0.5 s loop (no slicing, no
+    # converter job) - the kernel's own fraction of the INT8 peak, next to the whole-call figure of `roofline`
+    gemm_alone = None
+    if engine == 'f64_ozaki':
+        try:
+            from vittles_b200._cabi import check, ptr, require_cuda, stream
+            lib = require_cuda()
+            S_ = ops.OZAKI_SLICES
+            rows_c = min(37888, n_loc)
+            Bs, sb = ops.ozaki_slice(X[:rows_c], S_)
+            As, sa = ops.ozaki_slice(hinv, S_)
+            out_c = torch.empty((D, rows_c), dtype=torch.float64, device=dev)
+
+            def gemm_only():
+                check(lib.vt_ozaki_gemm(D, rows_c, D, ptr(As), As.stride(1), As.stride(0), ptr(Bs), Bs.stride(1),
+                                        Bs.stride(0), S_, -1.0, ptr(sa), ptr(sb), ptr(out_c), rows_c, stream()))
+            for _ in range(20):
+                gemm_only()
+            torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            nrep = 700
+            g0.record()
+            for _ in range(nrep):
+                gemm_only()
+            g1.record()
+            torch.cuda.synchronize()
+            ms_g = g0.elapsed_time(g1) / nrep
+            tops_g = 2.0 * D * D * rows_c * (S_ * (S_ + 1) // 2) / (ms_g * 1e-3) / 1e12
+            gemm_alone = {'kernel': 'ogemm_kernel<{}> (vt_ozaki_gemm on one pre-sliced chunk of {} observations)'.format(S_, rows_c),
+                          'launches': nrep, 'ms_per_launch': ms_g, 'achieved': tops_g, 'peak': i8_peak['tops'],
+                          'unit': 'INT8 TOP/s', 'frac': tops_g / i8_peak['tops'],
+                          'fp64_equiv_tflops': 2.0 * D * D * rows_c / (ms_g * 1e-3) / 1e12}
+            del Bs, As, out_c
+        except Exception as exc:                  # report, never hide
+            gemm_alone = {'error': repr(exc)[:200]}
     # conditioning of the Hessian at the optimum (reported: the fused path multiplies by an explicit inverse
     # only while kappa eps stays far below the parity tolerance - sensitivity_lib.EXPLICIT_INVERSE_MAX_COND)
     ev = torch.linalg.eigvalsh(H)
@@ -369,11 +404,14 @@ def main():
             peaks = json.load(f)
     except Exception:
         pass
-    traffic = None
+    traffic = traffic_i8 = None
     try:
         with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
-            traffic = json.load(f).get('ij_apply_dram_bytes_per_obs')
-            traffic = None if traffic is None else traffic * n_loc      # per launch at this run's shard size
+            tj = json.load(f)
+        traffic = tj.get('ij_apply_dram_bytes_per_obs')
+        traffic = None if traffic is None else traffic * n_loc      # per call at this run's shard size
+        traffic_i8 = tj.get('ogemm_apply_dram_bytes_per_obs')
+        traffic_i8 = None if traffic_i8 is None else traffic_i8 * n_loc
     except Exception:
         pass
 
@@ -471,7 +509,12 @@ def main():
                 'fp64_equivalent': {'achieved_tflops': apply_tflops, 'fp64_dmma_peak_tflops': peak_tflops,
                                     'ratio_to_fp64_pipe_peak': apply_tflops / peak_tflops,
                                     'algorithmic': '2*D^2 flop per observation'},
-                'traffic': None,
+                'gemm_kernel_alone': gemm_alone,
+                'traffic': traffic_i8,
+                'traffic_source': 'profiles/ncu_traffic.json: dram__bytes_read+write of one ncu --set full launch of '
+                                  'ogemm_kernel<7> (GEMM of a 37888-row chunk + in-kernel slicing of the next), scaled per '
+                                  'observation to the whole call; algorithmic = 30*D bytes/obs (8D x_n + 7D digits written '
+                                  '+ 7D digits read + 8D S_n)',
             }
         else:
             roofline = {'bound': 'tensor', 'kernel': 'dgemm_kernel<KC,KC> (vt_ij_apply: S = -Hinv G^T)',

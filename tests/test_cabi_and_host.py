@@ -183,3 +183,31 @@ def test_engine_selection_host_logic():
     assert lib.vt_syrk_tf32_workspace_bytes(10_000_000, 1024, 1) > 0
     assert lib.vt_tf32_gemm_workspace_bytes(1024, 1024, 1 << 20, 1) > 0     # long K: split-K partial tiles
     assert lib.vt_tf32_gemm_workspace_bytes(1024, 1 << 20, 1024, 1) == 0    # many tiles, short K: direct epilogue
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours) on a tiny shape: one JSON line with the
+    contract's keys, all host cores in use even when OMP_NUM_THREADS=1 is exported (as torch.distributed.run does)."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, OMP_NUM_THREADS='1')
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--dim', '16',
+                          '--cpu-sample', '3000', '--steps', '2', '--warmup', '1'], capture_output=True, text=True,
+                         env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith('{')]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+                'dtype', 'data', 'config', 'cpu_baseline', 'e2e'):
+        assert key in d, key
+    assert d['impl'] == 'reference' and d['steps'] == 2 and d['value'] > 0
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    ncores = len(os.sched_getaffinity(0))
+    assert d['cpu_baseline']['cores'] == ncores or ncores > 64      # every core, whatever OMP_NUM_THREADS says
+    # rank != 0 of a torchrun job exits quietly
+    out2 = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--dim', '16',
+                           '--cpu-sample', '3000'], capture_output=True, text=True, env=dict(env, RANK='1', WORLD_SIZE='2'),
+                          timeout=120)
+    assert out2.returncode == 0 and out2.stdout.strip() == ''

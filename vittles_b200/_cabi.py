@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, 'lib', 'libvittles_b200.so')
+LIB_PATH = os.environ.get('VT_LIB_PATH') or os.path.join(_PKG, 'lib', 'libvittles_b200.so')   # (override: A/B builds)
 
 VT_OK, VT_ERR_CUDA, VT_ERR_INVALID, VT_ERR_NOT_PD, VT_ERR_NO_CONVERGENCE = 0, 1, 2, 3, 4
 GLM_FAMILIES = {'logistic': 0, 'poisson': 1, 'gaussian': 2}

@@ -19,7 +19,10 @@ constexpr int O_EPI_WARPS = 8, O_CONV_WARPS = 8;
 constexpr int W_EPI0 = O_CONV_WARPS, W_TMA = O_CONV_WARPS + O_EPI_WARPS, W_MMA = W_TMA + 1;   // W_EPI0 % 4 == 0 (TMEM quarters)
 constexpr int A_TILE_BYTES = OBM * OBK;        // 16 KB: one slice of the A tile for one k-block
 constexpr int B_TILE_BYTES = OBN * OBK;        //  8 KB: one slice of the B tile for one k-block
-constexpr int A_RING = 4;                      // A slices stream through a 4-deep ring
+#ifndef VT_A_RING
+#define VT_A_RING 6
+#endif
+constexpr int A_RING = VT_A_RING;              // A slices stream through a ring of this depth
 constexpr int B_BUFS = 2;                      // all S slices of the B tile, double buffered over k-blocks
 
 template <int S>

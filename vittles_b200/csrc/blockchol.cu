@@ -77,8 +77,11 @@ __global__ void __launch_bounds__(128) block_potrf_kernel(double* blocks, long G
 // thread has all M loads of its column in flight before the substitution
 // starts (HBM bound: 16 M Dg bytes per block).
 constexpr int TRSM_BPC = 4;
+#ifndef VT_TRSM_MINB
+#define VT_TRSM_MINB 3
+#endif
 template <int MT, bool TR>
-__global__ void __launch_bounds__(256) block_trsm_kernel(const double* __restrict__ Lb, double* __restrict__ C, long G,
+__global__ void __launch_bounds__(256, MT <= 24 ? VT_TRSM_MINB : 1) block_trsm_kernel(const double* __restrict__ Lb, double* __restrict__ C, long G,
                                                          int M, int Dg) {
   __shared__ double sl[TRSM_BPC][MT * MT];
   __shared__ double sinv[TRSM_BPC][MT];
@@ -183,17 +186,28 @@ __global__ void __launch_bounds__(256) tall_gemv_kernel(const double* __restrict
 // ------------------------------------------------------------ tall colsum ----
 // partial[cta][c] = sum over the CTA's rows of u[r] * Z[r][c]
 constexpr int COLSUM_ROWS = 64;
-__global__ void __launch_bounds__(256) tall_colsum_kernel(const double* __restrict__ Z, long R, int Dg,
-                                                          const double* __restrict__ u, double* partial) {
+// The block is as wide as the matrix (up to 1024 columns per sweep: a 256-thread block left 3/4 of its threads idle
+// on the last 64 of 320 columns), and eight loads per thread are in flight (four accumulators, fixed order).
+__global__ void __launch_bounds__(1024) tall_colsum_kernel(const double* __restrict__ Z, long R, int Dg,
+                                                           const double* __restrict__ u, double* partial) {
   for (int c0 = 0; c0 < Dg; c0 += blockDim.x) {
     const int c = c0 + threadIdx.x;
-    double acc = 0.0;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     for (long rb = (long)blockIdx.x * COLSUM_ROWS; rb < R; rb += (long)gridDim.x * COLSUM_ROWS) {
       const long rend = rb + COLSUM_ROWS < R ? rb + COLSUM_ROWS : R;
-      if (c < Dg)
-        for (long r = rb; r < rend; ++r) acc = fma(u[r], Z[r * Dg + c], acc);
+      if (c < Dg) {
+        long r = rb;
+        for (; r + 8 <= rend; r += 8) {
+          double z[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) z[k] = Z[(r + k) * Dg + c];
+          a0 = fma(u[r], z[0], a0); a1 = fma(u[r + 1], z[1], a1); a2 = fma(u[r + 2], z[2], a2); a3 = fma(u[r + 3], z[3], a3);
+          a0 = fma(u[r + 4], z[4], a0); a1 = fma(u[r + 5], z[5], a1); a2 = fma(u[r + 6], z[6], a2); a3 = fma(u[r + 7], z[7], a3);
+        }
+        for (; r < rend; ++r) a0 = fma(u[r], Z[r * Dg + c], a0);
+      }
     }
-    if (c < Dg) partial[(long)blockIdx.x * Dg + c] = acc;
+    if (c < Dg) partial[(long)blockIdx.x * Dg + c] = (a0 + a1) + (a2 + a3);
   }
 }
 
@@ -306,6 +320,7 @@ int block_trsm(const double* Lb, double* C, long G, int M, int Dg, int transpose
   } while (0)
   if (M <= 8) VT_TRSM(8);
   else if (M <= 16) VT_TRSM(16);
+  else if (M <= 20) VT_TRSM(20);
   else if (M <= 24) VT_TRSM(24);
   else VT_TRSM(32);
 #undef VT_TRSM
@@ -333,9 +348,10 @@ size_t tall_colsum_workspace_bytes(int Dg) { return (size_t)num_sms() * 8 * Dg *
 int tall_colsum(const double* Z, long R, int Dg, const double* u, double alpha, const double* y0, double beta,
                 double* out, double* workspace, size_t workspace_bytes, cudaStream_t stream) {
   VT_REQUIRE(Z && u && out && R >= 1 && Dg >= 1, "tall_colsum: bad arguments");
-  const int grid = grid_for(R, COLSUM_ROWS, 8);
+  const int threads = Dg >= 1024 ? 1024 : (Dg + 31) / 32 * 32;
+  const int grid = grid_for(R, COLSUM_ROWS, threads > 512 ? 2 : (threads > 256 ? 4 : 8));
   VT_REQUIRE(workspace && workspace_bytes >= (size_t)grid * Dg * 8, "tall_colsum: workspace too small");
-  tall_colsum_kernel<<<grid, 256, 0, stream>>>(Z, R, Dg, u, workspace);
+  tall_colsum_kernel<<<grid, threads, 0, stream>>>(Z, R, Dg, u, workspace);
   VT_LAUNCH_CHECK();
   colsum_finish_kernel<<<(Dg + 255) / 256, 256, 0, stream>>>(workspace, grid, Dg, alpha, y0, beta, out);
   VT_LAUNCH_CHECK();

@@ -420,6 +420,11 @@ def main():
     freed = False
     if not args.no_e2e:
         try:
+            room0 = host_headroom_bytes()
+            need0 = int(1.15 * 8.0 * n_loc * D * (world if world > 1 else 1))
+            if room0 is not None and room0 < need0:
+                raise MemoryError('host memory headroom {:.0f} GB < {:.0f} GB needed to stage the inputs'.format(
+                    room0 / 1e9, need0 / 1e9))
             host = stage_to_host(torch, X, y, theta)
             # free every device-resident tensor of the resident phase: the e2e step brings its own
             obj.X = obj.y = obj = None
@@ -429,14 +434,27 @@ def main():
             torch.cuda.empty_cache()
             e2e = run_e2e(args, vt, torch, dist, dev, group, world, host)
             e2e['numa'] = numa_note
+            e2e['host_memory_headroom_gb_before_staging'] = None if room0 is None else room0 / 1e9
         except Exception as exc:      # report, never hide
             e2e = {'value': None, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0,
                    'error': repr(exc)[:300]}
         if e2e.get('value') and not args.no_e2e_full:
-            try:
-                e2e_full = run_e2e(args, vt, torch, dist, dev, group, world, host, full=True)
-            except Exception as exc:      # report, never hide (e.g. not enough pinnable host memory for X and S)
-                e2e_full = {'value': None, 'unit': UNIT, 'error': repr(exc)[:300]}
+            # the (D, N) result needs as much host memory again as the inputs already staged (all ranks of the node
+            # together); without clear headroom the leg is skipped - an out-of-memory kill would take the whole line
+            need = int(1.3 * 8.0 * N * D)
+            room = host_headroom_bytes()
+            ok = torch.tensor([1 if (room is None or room >= need) else 0], device=dev)
+            if world > 1:
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 1:
+                try:
+                    e2e_full = run_e2e(args, vt, torch, dist, dev, group, world, host, full=True)
+                except Exception as exc:      # report, never hide
+                    e2e_full = {'value': None, 'unit': UNIT, 'error': repr(exc)[:300]}
+            else:
+                e2e_full = {'value': None, 'unit': UNIT,
+                            'skipped': 'host memory headroom {:.0f} GB < {:.0f} GB needed to hold the (D, N) result next '
+                                       'to the staged inputs'.format((room or 0) / 1e9, need / 1e9)}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -615,6 +633,32 @@ def stage_to_host(torch, X, y, theta):
     w1 = torch.ones(n_loc, dtype=torch.float64)
     w1[::7] = 0.0
     return dict(X=X_host, y=y_host, w=w_host, w1=w1.pin_memory(), theta=theta.cpu().pin_memory())
+
+
+def host_headroom_bytes():
+    """Bytes of host memory this process may still take: the smaller of the system's available memory and the
+    headroom of the memory cgroup it runs in (pinned pages count against both).  The e2e legs stage 82 GB of inputs
+    - and e2e_full another 82 GB of results - in host memory; taking more than there is gets the whole process
+    killed (and the bench line with it), so those legs check first and report why they were skipped."""
+    avail = None
+    try:
+        import psutil
+        avail = int(psutil.virtual_memory().available)
+    except Exception:
+        pass
+    for lim_path, cur_path in (('/sys/fs/cgroup/memory.max', '/sys/fs/cgroup/memory.current'),
+                               ('/sys/fs/cgroup/memory/memory.limit_in_bytes', '/sys/fs/cgroup/memory/memory.usage_in_bytes')):
+        try:
+            with open(lim_path) as f:
+                lim = f.read().strip()
+            with open(cur_path) as f:
+                cur = int(f.read().strip())
+            if lim != 'max' and int(lim) < (1 << 60):
+                room = int(lim) - cur
+                avail = room if avail is None else min(avail, room)
+        except Exception:
+            continue
+    return avail
 
 
 def numa_bind_to_gpu(local_rank):

@@ -223,3 +223,28 @@ def test_cg_preconditioner_x0_and_callback(vt):
     with pytest.warns(UserWarning, match='CG exited with error code 3'):
         vt.solver_lib.get_cg_solver(mv, d, {'maxiter': 3})(b)
     assert_close(x_plain, ref, rtol=1e-6, atol_scale=1e-8)
+
+
+def test_linear_approximation_with_one_hyperparameter_and_a_cg_solver(vt):
+    """a scalar hyperparameter gives a (D, 1) cross-Hessian; with a CG ``hess_solver`` the sensitivity
+    matrix must stay (D, 1) (it used to collapse to 1-d and break the prediction)."""
+    from vittles_b200.sensitivity_lib import EstimatingEquationLinearApproximation
+    rng = np.random.RandomState(2)
+    d = 12
+    a = rng.normal(size=(d, d + 3))
+    A = a @ a.T / d + np.eye(d)
+    c = rng.normal(size=d)
+    Ad, cd = _dev(A), _dev(c)
+
+    def estimating_equation(theta, lam):          # root: theta = -A^{-1} c lam
+        return Ad.to(theta.device) @ theta + cd.to(theta.device) * lam[0]
+    lam0 = np.array([0.7])
+    theta0 = -np.linalg.solve(A, c) * lam0[0]
+    solver = vt.solver_lib.get_cg_solver(lambda v: Ad @ v if isinstance(v, torch.Tensor) else A @ v, d, {'tol': 1e-13})
+    lin = EstimatingEquationLinearApproximation(estimating_equation, theta0, lam0, solver, validate_solution=True,
+                                                solution_tol=1e-9)
+    S = lin.get_dinput_dhyper()
+    assert S.shape == (d, 1)
+    assert_close(S[:, 0], -np.linalg.solve(A, c), rtol=1e-8, atol_scale=1e-11)
+    assert_close(lin.predict_input_par_from_hyper_par(np.array([1.1])), -np.linalg.solve(A, c) * 1.1, rtol=1e-8,
+                 atol_scale=1e-11)

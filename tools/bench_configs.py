@@ -196,7 +196,12 @@ def config4(cx, D=4096, Kmom=2048):
     k0, k1 = (Kmom * cx.rank) // cx.world, (Kmom * (cx.rank + 1)) // cx.world
     Jl = J[k0:k1].contiguous()
     res = {'config': 'LinearResponseCovariances D={}, {} moments, moment columns over {} rank(s)'.format(D, Kmom, cx.world)}
-    t_f, fac = cx.timed(lambda: ops.potrf(H), reps=3)
+    Lbuf = torch.empty_like(H)
+
+    def factor():                                   # into a preallocated buffer (the 134 MB copy of H is 0.05 ms)
+        Lbuf.copy_(H)
+        return ops.potrf(Lbuf, overwrite=True)
+    t_f, fac = cx.timed(factor, reps=5, warm=2)
     res['potrf'] = {'ms': t_f, 'tflops': D ** 3 / 3.0 / t_f / 1e9, 'frac_fp64_peak': D ** 3 / 3.0 / t_f / 1e9 / cx.peak}
     Jt = Jl.T.contiguous()
     t_s, X = cx.timed(lambda: fac.solve(Jt), reps=3)

@@ -59,6 +59,14 @@ STAGING_BYTES = 512 << 20
 def _to_host_staged(src):
     flat = src.reshape(-1)
     n = flat.numel()
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = None
+    if avail is not None and n * src.element_size() > 0.9 * avail:
+        raise MemoryError('the result ({:.1f} GB) does not fit in the available host memory ({:.1f} GB); keep it on the '
+                          'device (pass CUDA tensors in, get CUDA tensors back)'.format(n * src.element_size() / 1e9, avail / 1e9))
     out = torch.empty(n, dtype=src.dtype)
     per = max(1, STAGING_BYTES // src.element_size())
     stage = [torch.empty(min(per, n), dtype=src.dtype, pin_memory=True) for _ in range(2)]

@@ -106,39 +106,38 @@ __device__ __forceinline__ OUnit o_decode(const OKernelArgs& a, long u) {
 // of `nslices`) of four values is packed with PRMT into one word (byte j = value j).
 // (oracle/slicing.py is the CPU model; tests/test_gpu_ozaki.py compares digit for digit.)
 struct Fixed4 {
-  uint32_t lo[4], hi[4];       // the two halves of u ^ B
+  uint32_t lo[4], hi[4];       // biased digits: positions 0..2 in bytes 0..2 of lo, positions 3..S-1 in the bytes of hi
 };
-__host__ __device__ constexpr unsigned long long digit_bias(int nslices) {
-  return 0x8080808080808080ULL >> (8 * (8 - nslices));
-}
+// bias of the S - 3 digits kept in the high word
+__host__ __device__ constexpr uint32_t digit_bias_hi(int nslices) { return 0x80808080u >> (8 * (7 - nslices)); }
 // t = x * 2^(8S-2) / sigma, |t| <= 2^(8S-2).  Round-to-nearest-even through the FP64 adder: v + 1.5 2^52 holds
 // rint(v) in the low word of its significand for |v| < 2^51 (no conversion instructions: those issue at a quarter
-// of the FP64 rate).
-__device__ __forceinline__ void fixed4_set(Fixed4& f, int j, double t, unsigned long long bias) {
+// of the FP64 rate).  q = hi 2^24 + lo with |lo| <= 2^23; the balanced digits of lo are the bytes of lo + 0x808080
+// minus 128 each, and what that sum carries beyond 24 bits (0 or 1) goes to hi - everything in 32-bit integers.
+__device__ __forceinline__ void fixed4_set(Fixed4& f, int j, double t, uint32_t bias_hi) {
   constexpr double MAGIC = 6755399441055744.0;                       // 1.5 * 2^52
   const double mh = fma(t, 1.0 / 16777216.0, MAGIC);                // rint(t 2^-24), |.| <= 2^30
   const int hi = __double2loint(mh);
   const double rem = fma(-(mh - MAGIC), 16777216.0, t);             // exact, |rem| <= 2^23
   const int lo = __double2loint(rem + MAGIC);
-  const long long q = ((long long)hi << 24) + (long long)lo;
-  const unsigned long long u = ((unsigned long long)q + bias) ^ bias;
-  f.lo[j] = (uint32_t)u;
-  f.hi[j] = (uint32_t)(u >> 32);
+  const uint32_t ulo = (uint32_t)lo + 0x00808080u;                  // in [0x8080, 0x1008080]
+  f.lo[j] = ulo;
+  f.hi[j] = (uint32_t)hi + (ulo >> 24) + bias_hi;
 }
 template <int S>
 __device__ __forceinline__ uint32_t fixed4_digits(const Fixed4& f, int sl) {
-  const int pos = S - 1 - sl;                      // byte position from the least significant one
-  const uint32_t sel = (uint32_t)(pos & 3);
+  const int pos = S - 1 - sl;                      // digit position from the least significant one
+  const uint32_t sel = (uint32_t)(pos < 3 ? pos : pos - 3);
   const uint32_t pick = sel | ((4u + sel) << 4);   // PRMT: byte `sel` of the first source, byte `sel` of the second
   uint32_t p01, p23;
-  if (pos < 4) {
+  if (pos < 3) {
     p01 = __byte_perm(f.lo[0], f.lo[1], pick);
     p23 = __byte_perm(f.lo[2], f.lo[3], pick);
   } else {
     p01 = __byte_perm(f.hi[0], f.hi[1], pick);
     p23 = __byte_perm(f.hi[2], f.hi[3], pick);
   }
-  return __byte_perm(p01, p23, 0x5410);
+  return __byte_perm(p01, p23, 0x5410) ^ 0x80808080u;      // biased byte e -> digit e - 128
 }
 
 // One warp per row: row maximum -> power-of-two scale -> S balanced base-256 digits,
@@ -146,7 +145,7 @@ __device__ __forceinline__ uint32_t fixed4_digits(const Fixed4& f, int sl) {
 // Rows of at most 128 * RC elements are held in registers between the two passes (RC = 0: re-read).
 template <int S, int RC>
 __device__ __forceinline__ void slice_one_row(const SliceJob& jb, long r, int lane, bool vec) {
-  constexpr unsigned long long bias = digit_bias(S);
+  constexpr uint32_t bias = digit_bias_hi(S);
   const double* xr = jb.X + r * jb.ldx;
   const int cols = jb.cols;
   double m = 0.0;
@@ -536,7 +535,7 @@ __global__ void __launch_bounds__(256) ozaki_slice_t_kernel(const double* __rest
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long tiles_x = (rows + ST_OBS - 1) / ST_OBS;
   const int tiles_y = (cols + ST_FEAT - 1) / ST_FEAT;
-  constexpr unsigned long long bias = digit_bias(S);
+  constexpr uint32_t bias = digit_bias_hi(S);
   for (long tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
     const long n0 = (tile / tiles_y) * ST_OBS;          // feature blocks fastest: a CTA wave reads whole rows of X
     const int i0 = (int)(tile % tiles_y) * ST_FEAT;

@@ -79,10 +79,14 @@ inline size_t xtfx_smem_bytes(int Dp, int R, int Q) {
 // NOUT = 1: one output vector, u_n = op(n, t, aux).  NOUT = Q > 1: Q output vectors, op.multi(n, t, aux, u) fills
 // u_j - the accumulators of all Q outputs live in registers, so the CTA count per SM drops to one.
 // CMAX: additionally keep max_n q_n |x_nc| per column, q_n the second value of op.stats2 (the column scales of the
-// INT8 slicing engine's Hessian assembly come out of the statistics pass instead of a sweep of their own); a
-// non-finite product poisons its column with NaN (fmax alone would drop it).
-__device__ __forceinline__ double xt_nanmax(double m, double v) {
-  return (v <= 1.7976931348623157e308 && m == m) ? fmax(m, v) : __longlong_as_double(0x7ff8000000000000LL);
+// INT8 slicing engine's Hessian assembly come out of the statistics pass instead of a sweep of their own).  Only
+// the binade of the maximum matters (the scale is the next power of two), so the maximum is taken over the HIGH
+// words of the products as unsigned integers - sign 0, exponent, top 20 bits of the significand: one integer
+// instruction per element, the exponent of the result is exact, and Inf / NaN (exponent all ones) are above every
+// finite value, so a non-finite product poisons its column as the engine's own sweep does.
+__device__ __forceinline__ uint32_t xt_himax(uint32_t m, double v) {
+  const uint32_t h = (uint32_t)__double2hiint(v);
+  return h > m ? h : m;
 }
 template <class RowOp, int Q, int CPT, int R, int NOUT = 1, bool CMAX = false>
 __global__ void __launch_bounds__(XT_THREADS, (R * CPT <= 8 && NOUT == 1) ? 2 : 1) xtfx_kernel(const XtfxParams p, const RowOp op) {
@@ -134,9 +138,9 @@ __global__ void __launch_bounds__(XT_THREADS, (R * CPT <= 8 && NOUT == 1) ? 2 : 
   for (int o = 0; o < NOUT; ++o)
 #pragma unroll
     for (int i = 0; i < CPT; ++i) acc[o][i] = make_double2(0.0, 0.0);
-  double2 cmx[CMAX ? CPT : 1];
+  uint32_t cmx[CMAX ? 2 * CPT : 1];
 #pragma unroll
-  for (int i = 0; i < (CMAX ? CPT : 1); ++i) cmx[i] = make_double2(0.0, 0.0);
+  for (int i = 0; i < (CMAX ? 2 * CPT : 1); ++i) cmx[i] = 0u;
 
   if (p.bulk && tid == 0) {
     for (int s = 0; s < XT_NBUF; ++s) {
@@ -238,8 +242,8 @@ __global__ void __launch_bounds__(XT_THREADS, (R * CPT <= 8 && NOUT == 1) ? 2 : 
           const double q = s_q[r];
 #pragma unroll
           for (int i = 0; i < CPT; ++i) {
-            cmx[i].x = xt_nanmax(cmx[i].x, q * fabs(x[r][i].x));
-            cmx[i].y = xt_nanmax(cmx[i].y, q * fabs(x[r][i].y));
+            cmx[2 * i] = xt_himax(cmx[2 * i], q * fabs(x[r][i].x));
+            cmx[2 * i + 1] = xt_himax(cmx[2 * i + 1], q * fabs(x[r][i].y));
           }
         }
       }
@@ -258,7 +262,9 @@ __global__ void __launch_bounds__(XT_THREADS, (R * CPT <= 8 && NOUT == 1) ? 2 : 
 #pragma unroll
       for (int i = 0; i < CPT; ++i) {
         const int c = 2 * tid + 512 * i;
-        if (c < Dp) *reinterpret_cast<double2*>(p.partial_max + (size_t)blockIdx.x * Dp + c) = cmx[i];
+        if (c < Dp)
+          *reinterpret_cast<double2*>(p.partial_max + (size_t)blockIdx.x * Dp + c) =
+              make_double2(__hiloint2double((int)cmx[2 * i], 0), __hiloint2double((int)cmx[2 * i + 1], 0));
       }
     }
   }

@@ -406,6 +406,8 @@ int gemm_pick_parts(int ntiles, int kiters, int tile, size_t workspace_bytes) {
   return best;
 }
 
+int gemm_ctas_per_sm(int tile) { return ctas_per_sm(tile); }
+
 size_t gemm_workspace_bytes(int M, int N, int K, int lower, int tile) {
   if (tile == 0) tile = gemm_pick_tile(M, N, K, lower);
   const int ntiles = count_tiles(M, N, lower, tile);
@@ -438,7 +440,9 @@ int gemm_launch(GemmParams p, cudaStream_t stream) {
                p.parts, p.ntiles);
   const long units = (long)p.ntiles * p.parts;
   const long slots = (long)num_sms() * ctas_per_sm(p.tile);
-  const int grid = (int)(units < slots ? units : slots);
+  long cap = slots - (long)p.spare_sms * ctas_per_sm(p.tile);
+  if (cap < ctas_per_sm(p.tile)) cap = ctas_per_sm(p.tile);
+  const int grid = (int)(units < cap ? units : cap);
   int st;
   if (p.kscale) {
     VT_REQUIRE(p.amode == KS && p.bmode == KS, "gemm: kscale is only implemented for KS x KS operands");

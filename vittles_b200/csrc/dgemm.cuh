@@ -49,6 +49,7 @@ struct GemmParams {
   int mirror;      // lower only: also write C(n,m) = C(m,n) (symmetric result)
   int parts;       // split-K factor (>= 1); 0 = choose automatically
   int tile;        // CTA tile edge: TILE_BIG, TILE_SMALL, or 0 = choose automatically
+  int spare_sms;   // leave this many SMs without a CTA of the persistent grid (room for a concurrent kernel)
   double* workspace; size_t workspace_bytes;
   // derived (filled by gemm_launch)
   int tiles_m, tiles_n, ntiles, kiters, a_vec, b_vec, c_vec;
@@ -61,5 +62,6 @@ size_t gemm_workspace_bytes(int M, int N, int K, int lower, int tile);
 // Tile edge chosen for a shape when GemmParams::tile == 0.
 int gemm_pick_tile(int M, int N, int K, int lower);
 int gemm_pick_parts(int ntiles, int kiters, int tile, size_t workspace_bytes);
+int gemm_ctas_per_sm(int tile);
 
 }  // namespace vt

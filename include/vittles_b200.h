@@ -169,16 +169,27 @@ int vt_syrk_tf32(const double* X, int64_t ldx, int64_t N, int D, const double* s
 /* ---- FP64-grade contraction on the INT8 tensor cores (error-free slicing) ------
  * An additional engine for the H^{-1} G^T apply (precision 'f64_ozaki'): every
  * row of both operands is scaled by a power of two and cut into `nslices`
- * (6..8) signed 7-bit digits (vt_ozaki_slice: out[s][r][k] int8, scale_out[r] =
- * 2^e_r * fold[r]); the nslices (nslices + 1) / 2 significant digit products
- * run exactly on tcgen05.mma.kind::i8 with INT32 accumulators in TMEM and are
- * recombined in INT64 / FP64 in the epilogue (vt_ozaki_gemm, K <= 16384).  With
- * 7 slices the result is within ~1e-11 of sigma_m tau_n (the row scales), i.e.
- * inside the rtol 1e-8 parity bar of the FP64 path; 8 slices give ~1e-13.
- * vt_ij_apply_ozaki is vt_ij_apply on this engine (observations sliced chunk by
- * chunk inside).                                                               */
+ * (5..7) balanced base-256 digits in [-128, 127] (vt_ozaki_slice: out[s][r][k]
+ * int8, scale_out[r] = 2^e_r * fold[r]); the nslices (nslices + 1) / 2
+ * significant digit products run exactly on tcgen05.mma.kind::i8 with INT32
+ * accumulators in TMEM and are recombined in INT64 / FP64 in the epilogue
+ * (vt_ozaki_gemm, K <= 16384).  With 7 slices (54 bits) the result is within
+ * ~1e-14 of sigma_m tau_n K (the row scales), inside the rtol 1e-8 parity bar
+ * of the FP64 path.  vt_ij_apply_ozaki is vt_ij_apply on this engine; the
+ * observations are sliced chunk by chunk by converter warps inside the GEMM
+ * kernel, with integer instructions only (FP64 instructions starve while the
+ * tensor pipe is saturated).  vt_ozaki_slice_int runs that instruction
+ * sequence as a kernel of its own (cols <= 1024; same digits), and
+ * vt_ozaki_slice_t writes the Hessian's operand: digits of sq[n] * X[n][i]
+ * TRANSPOSED, out[s][i][n], one scale per feature from colmax[i] (the bit
+ * pattern of max_n |sq[n] X[n][i]|), integer_variant as above.               */
 int vt_ozaki_slice(const double* X, int64_t ldx, int64_t rows, int cols, int8_t* out, int64_t ldo, int64_t slice_stride,
                    int nslices, double* scale_out, const double* fold, void* stream);
+int vt_ozaki_slice_int(const double* X, int64_t ldx, int64_t rows, int cols, int8_t* out, int64_t ldo, int64_t slice_stride,
+                       int nslices, double* scale_out, const double* fold, void* stream);
+int vt_ozaki_slice_t(const double* X, int64_t ldx, int64_t rows, int cols, const double* sq, const uint64_t* colmax,
+                     int8_t* out, int64_t ldo, int64_t slice_stride, int nslices, double* scale_out, int integer_variant,
+                     void* stream);
 int vt_ozaki_gemm(int M, int N, int K, const int8_t* A, int64_t lda, int64_t a_slice_stride, const int8_t* B,
                   int64_t ldb, int64_t b_slice_stride, int nslices, double alpha, const double* rowscale,
                   const double* colscale, double* C, int64_t ldc, void* stream);

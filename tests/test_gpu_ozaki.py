@@ -59,6 +59,59 @@ def test_digits_and_products_match_the_cpu_model_exactly(vt, S):
     assert np.array_equal(out, model)
 
 
+def _awkward_matrix(rows, cols, S, seed):
+    """Values that exercise the rounding of the slicers: exact ties at the last digit, subnormals, zeros, the row
+    maximum itself (a power of two: the largest fixed-point value), all of mixed sign."""
+    X = _rnd(rows, cols, seed=seed) * torch.exp(4 * _rnd(rows, 1, seed=seed + 1))
+    ulp = 2.0 ** -(8 * S - 2)                     # one unit of the last digit relative to the row scale
+    X[0, :] = 0.0
+    X[1, 0] = 1.0 - 2.0 ** -53                    # just below the scale 1: the largest q
+    X[1, 1:9] = torch.tensor([0.5, 1.5, 2.5, 3.5, -0.5, -1.5, -2.5, 127.5], device='cuda', dtype=torch.float64) * ulp
+    X[1, 9:] = X[1, 9:].clamp(-0.9, 0.9)
+    X[2, :] = 5e-324 * torch.arange(cols, device='cuda', dtype=torch.float64)       # subnormal row
+    X[3, 0], X[3, 1], X[3, 2] = 1e300, 1e-300, -4.9e-324                            # 600 orders of magnitude apart
+    X[4, :] = -2.0 ** -3                          # every entry the negative of a power of two
+    return X
+
+
+@pytest.mark.parametrize('S', [5, 6, 7])
+def test_integer_slicer_writes_the_same_digits(vt, S):
+    """The converter warps of the GEMM kernel slice with integer instructions only; their sequence, run as a kernel
+    of its own, must reproduce the FP64 slicer (and so the oracle's model) digit for digit."""
+    from oracle import slicing
+    X = _awkward_matrix(200, 520, S, seed=40)
+    d_fp, sc_fp = vt.ops.ozaki_slice(X, S)
+    d_int, sc_int = vt.ops.ozaki_slice(X, S, integer_variant=True)
+    assert torch.equal(sc_fp, sc_int)
+    assert torch.equal(d_fp, d_int)
+    d_ref, sc_ref = slicing.slice_rows(X.cpu().numpy(), S)
+    assert np.array_equal(d_int[:, :, :520].cpu().numpy(), d_ref)
+    assert np.array_equal(sc_int.cpu().numpy(), sc_ref)
+    with pytest.raises(Exception):
+        vt.ops.ozaki_slice(_rnd(4, 1100), S, integer_variant=True)
+
+
+@pytest.mark.parametrize('S', [5, 7])
+@pytest.mark.parametrize('shape', [(1000, 70), (257, 33), (16, 520)])
+def test_transposed_slicer_variants_match_the_cpu_model(vt, S, shape):
+    """Digits of sqrt(s_n) x_ni written observation-contiguous with one scale per feature: both instruction
+    sequences against the oracle's row slicer applied to the transposed weighted matrix."""
+    from oracle import slicing
+    N, D = shape
+    X = _rnd(N, D, seed=50) * torch.exp(2 * _rnd(1, D, seed=51))
+    X[3, :] = 0.0
+    X[:, 2] = 0.0                                                       # a feature that is zero everywhere
+    sq = torch.rand(N, device='cuda', dtype=torch.float64, generator=torch.Generator(device='cuda').manual_seed(52)).sqrt()
+    d_fp, sc_fp = vt.ops.ozaki_slice_t(X, sq, S)
+    d_int, sc_int = vt.ops.ozaki_slice_t(X, sq, S, integer_variant=True)
+    assert torch.equal(sc_fp, sc_int) and torch.equal(d_fp, d_int)
+    W = (X * sq[:, None]).T.contiguous().cpu().numpy()                  # the same FP64 products
+    d_ref, sc_ref = slicing.slice_rows(W, S)
+    assert np.array_equal(d_int[:, :, :N].cpu().numpy(), d_ref)
+    assert np.array_equal(sc_int.cpu().numpy(), sc_ref)
+    assert bool((d_int[:, :, N:] == 0).all())
+
+
 def test_extreme_digits_do_not_overflow_int32(vt):
     """All digits -128 over the longest K one accumulation may see (16384): the INT32 accumulators hold
     7 K 2^14 < 2^31 (checked through the raw digit GEMM entry point against the integer model)."""

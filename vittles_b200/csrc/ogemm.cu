@@ -35,6 +35,8 @@ struct SliceJob {
   const double* X; long ldx; long rows; int cols;
   int8_t* out; long ldo; long slice_stride;
   double* scale_out; const double* fold;
+  // transposed job (colmax != nullptr): out[s][feature][observation] of sq_n x_ni, one scale per feature
+  const double* sq; const unsigned long long* colmax;
 };
 
 struct OKernelArgs {
@@ -51,6 +53,7 @@ struct OKernelArgs {
   const double* colscale;
   int c_vec;
   SliceJob next;                // rows to slice during this launch (X == nullptr: none; cols <= 1024)
+  unsigned epi_sleep_ns;        // the epilogue warps poll for the accumulators this often (0: spin)
   unsigned long long* timing;   // development aid (VT_OGEMM_TIMING=1): clocks the MMA thread waits, summed over CTAs
 };
 
@@ -124,13 +127,35 @@ __device__ __forceinline__ void fixed4_set(Fixed4& f, int j, double t, uint32_t 
   f.lo[j] = ulo;
   f.hi[j] = (uint32_t)hi + (ulo >> 24) + bias_hi;
 }
-template <int S>
+// The same digits with integer instructions only, for the converter warps of the GEMM kernel: while the tensor
+// pipe is saturated, FP64 instructions of other warps wait ~60 clocks each for their pipe (ncu: stall_math_pipe_throttle
+// on every DMUL / DFMA / DADD of the converters), the integer pipe is idle.  x = +-M 2^(eb - 1075) with the 53-bit
+// significand M, so t = 2M >> n with n = k2 - eb, k2 = e + 1078 - 8S, rounded to nearest even by adding half an ulp
+// minus one plus the bit that would become the last (n >= 0 because |x| < 2^e, except in a row whose maximum is
+// subnormal, where the shift goes left).  Here lo holds the positions 0..3 and hi the positions 4..S-1 (NLO = 4 in
+// fixed4_digits).
+__host__ __device__ constexpr unsigned long long digit_bias64(int nslices) { return 0x8080808080808080ULL >> (8 * (8 - nslices)); }
+__device__ __forceinline__ void fixed4_set_bits(Fixed4& f, int j, unsigned long long bits, int k2, unsigned long long bias64) {
+  const int eb = (int)((bits >> 52) & 0x7ffULL);
+  unsigned long long m = bits & 0x000fffffffffffffULL;
+  m = (eb ? (m | 0x0010000000000000ULL) : m) << 1;             // subnormal: exponent 1, no hidden bit
+  const int n0 = k2 - (eb ? eb : 1);
+  const int n = n0 < 0 ? 0 : (n0 > 63 ? 63 : n0);              // right shift; left shift only under a subnormal maximum
+  const int nl = n0 < 0 ? (n0 < -63 ? 63 : -n0) : 0;           // (rows with Inf / NaN, whose scale is NaN, get garbage)
+  const unsigned long long last = (m >> n) & 1ULL;
+  const unsigned long long add = n ? ((1ULL << (n - 1)) - 1ULL + last) : 0ULL;
+  const unsigned long long q = ((m + add) >> n) << nl;
+  const unsigned long long u = ((long long)bits < 0 ? 0ULL - q : q) + bias64;
+  f.lo[j] = (uint32_t)u;
+  f.hi[j] = (uint32_t)(u >> 32);
+}
+template <int S, int NLO = 3>
 __device__ __forceinline__ uint32_t fixed4_digits(const Fixed4& f, int sl) {
   const int pos = S - 1 - sl;                      // digit position from the least significant one
-  const uint32_t sel = (uint32_t)(pos < 3 ? pos : pos - 3);
+  const uint32_t sel = (uint32_t)(pos < NLO ? pos : pos - NLO);
   const uint32_t pick = sel | ((4u + sel) << 4);   // PRMT: byte `sel` of the first source, byte `sel` of the second
   uint32_t p01, p23;
-  if (pos < 3) {
+  if (pos < NLO) {
     p01 = __byte_perm(f.lo[0], f.lo[1], pick);
     p23 = __byte_perm(f.lo[2], f.lo[3], pick);
   } else {
@@ -143,8 +168,10 @@ __device__ __forceinline__ uint32_t fixed4_digits(const Fixed4& f, int sl) {
 // One warp per row: row maximum -> power-of-two scale -> S balanced base-256 digits,
 // so that 2^-6 sum_s d_s 2^{-8s} reproduces x / sigma to 8 S - 2 bits (round to nearest).
 // Rows of at most 128 * RC elements are held in registers between the two passes (RC = 0: re-read).
-template <int S, int RC>
+// INTEGER: maximum and digits with integer instructions only (fixed4_set_bits; same digits).
+template <int S, int RC, bool INTEGER = false>
 __device__ __forceinline__ void slice_one_row(const SliceJob& jb, long r, int lane, bool vec) {
+  static_assert(!INTEGER || RC > 0, "the integer slicer keeps the row in registers");
   constexpr uint32_t bias = digit_bias_hi(S);
   const double* xr = jb.X + r * jb.ldx;
   const int cols = jb.cols;
@@ -163,14 +190,33 @@ __device__ __forceinline__ void slice_one_row(const SliceJob& jb, long r, int la
         for (int j = 0; j < 4; ++j) xv[ch][j] = (c0 + j < cols) ? xr[c0 + j] : 0.0;
       }
     }
+    if constexpr (INTEGER) {
+      // |x| as an unsigned integer orders like the double; Inf and NaN sit above every finite value
+      unsigned long long mb = 0ULL;
 #pragma unroll
-    for (int ch = 0; ch < RC; ++ch)
+      for (int ch = 0; ch < RC; ++ch)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const double v = fabs(xv[ch][j]);
-        finite = finite && (v <= 1.7976931348623157e308);
-        m = fmax(m, v);
+        for (int j = 0; j < 4; ++j) {
+          const unsigned long long b = (unsigned long long)__double_as_longlong(xv[ch][j]) & 0x7fffffffffffffffULL;
+          mb = b > mb ? b : mb;
+        }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, mb, o);
+        mb = other > mb ? other : mb;
       }
+      finite = mb < 0x7ff0000000000000ULL;
+      m = finite ? __longlong_as_double((long long)mb) : 0.0;
+    } else {
+#pragma unroll
+      for (int ch = 0; ch < RC; ++ch)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const double v = fabs(xv[ch][j]);
+          finite = finite && (v <= 1.7976931348623157e308);
+          m = fmax(m, v);
+        }
+    }
   } else {
     for (int c = lane; c < cols; c += 32) {
       const double v = fabs(xr[c]);
@@ -178,12 +224,16 @@ __device__ __forceinline__ void slice_one_row(const SliceJob& jb, long r, int la
       m = fmax(m, v);
     }
   }
+  if constexpr (!INTEGER) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-  finite = __all_sync(0xffffffffu, finite);
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    finite = __all_sync(0xffffffffu, finite);
+  }
   int e = 0;
   if (finite && m > 0.0) (void)frexp(m, &e);         // m = f 2^e, f in [0.5, 1)  ->  |x| 2^-e < 1
-  const double up = ldexp(1.0, 8 * S - 2 - e);       // |x * up| <= 2^(8S-2)
+  // |x * up * up2| <= 2^(8S-2); the power of two goes in two factors because rows below ~1e-290 need more than 2^1023
+  const int sh = 8 * S - 2 - e;
+  const double up = ldexp(1.0, sh > 1000 ? 1000 : sh), up2 = ldexp(1.0, sh > 1000 ? sh - 1000 : 0);
   // a row with an Inf or NaN gets a NaN scale: every result that touches it is NaN, as in FP64 arithmetic
   if (lane == 0)
     jb.scale_out[r] = finite ? ldexp(1.0, e) * (jb.fold ? jb.fold[r] : 1.0) : __longlong_as_double(0x7ff8000000000000LL);
@@ -195,18 +245,27 @@ __device__ __forceinline__ void slice_one_row(const SliceJob& jb, long r, int la
       const int c0 = ch * 128 + lane * 4;
       if (c0 < jb.ldo) {
         Fixed4 f;
+        if constexpr (INTEGER) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) fixed4_set(f, j, xv[ch][j] * up, bias);
+          for (int j = 0; j < 4; ++j)
+            fixed4_set_bits(f, j, (unsigned long long)__double_as_longlong(xv[ch][j]), e + 1078 - 8 * S, digit_bias64(S));
 #pragma unroll
-        for (int s = 0; s < S; ++s)
-          *reinterpret_cast<uint32_t*>(orow + (long)s * jb.slice_stride + c0) = fixed4_digits<S>(f, s);
+          for (int s = 0; s < S; ++s)
+            *reinterpret_cast<uint32_t*>(orow + (long)s * jb.slice_stride + c0) = fixed4_digits<S, 4>(f, s);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) fixed4_set(f, j, xv[ch][j] * up * up2, bias);
+#pragma unroll
+          for (int s = 0; s < S; ++s)
+            *reinterpret_cast<uint32_t*>(orow + (long)s * jb.slice_stride + c0) = fixed4_digits<S>(f, s);
+        }
       }
     }
   } else {
     for (int c0 = lane * 4; c0 < jb.ldo; c0 += 128) {
       Fixed4 f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) fixed4_set(f, j, (c0 + j < cols) ? xr[c0 + j] * up : 0.0, bias);
+      for (int j = 0; j < 4; ++j) fixed4_set(f, j, (c0 + j < cols) ? xr[c0 + j] * up * up2 : 0.0, bias);
 #pragma unroll
       for (int s = 0; s < S; ++s)
         *reinterpret_cast<uint32_t*>(orow + (long)s * jb.slice_stride + c0) = fixed4_digits<S>(f, s);
@@ -214,13 +273,86 @@ __device__ __forceinline__ void slice_one_row(const SliceJob& jb, long r, int la
   }
 }
 
-template <int S, int RC>
+template <int S, int RC, bool INTEGER = false>
 __global__ void __launch_bounds__(256) ozaki_slice_kernel(const SliceJob jb) {
   const int lane = threadIdx.x & 31;
   const long warp0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
   const bool vec = (jb.ldx % 2 == 0) && (reinterpret_cast<uintptr_t>(jb.X) % 16 == 0);
-  for (long r = warp0; r < jb.rows; r += nwarps) slice_one_row<S, RC>(jb, r, lane, vec);
+  for (long r = warp0; r < jb.rows; r += nwarps) slice_one_row<S, RC, INTEGER>(jb, r, lane, vec);
+}
+
+// Tile of 32 observations x 32 features per warp, lane = feature: 32 coalesced 256-byte reads (all in flight at
+// once), the 32 values of a feature stay in the lane's registers, and the digits of 16 consecutive observations of
+// one slice leave as one 16-byte store (two per 32-byte sector, back to back) - the transposition costs no shared
+// memory, so the converter warps of the GEMM kernel can run it next to the operand ring.  Observations past `rows`
+// are written as zeros up to the next multiple of 16 (the GEMM's tensor map ends at `rows` anyway).
+constexpr int ST_OBS = 32, ST_FEAT = 32, ST_GROUP = 8;      // a CTA step: ST_GROUP consecutive tiles along the observations
+template <int S, bool INTEGER>
+__device__ __forceinline__ void slice_t_tile(const SliceJob& jb, long n0, int i0, int lane, bool first) {
+  constexpr uint32_t bias = digit_bias_hi(S);
+  const int i = i0 + lane;
+  const bool live = i < jb.cols;
+  int e = 0;
+  if (live) {
+    const double m = __longlong_as_double((long long)jb.colmax[i]);
+    const bool finite = m <= 1.7976931348623157e308;
+    if (finite && m > 0.0) (void)frexp(m, &e);
+    if (first) jb.scale_out[i] = finite ? ldexp(1.0, e) : m;   // NaN scale: row and column i of H become NaN
+  }
+  const int sh = 8 * S - 2 - e;
+  const double up = ldexp(1.0, sh > 1000 ? 1000 : sh), up2 = ldexp(1.0, sh > 1000 ? sh - 1000 : 0);   // (see slice_one_row)
+  double xv[ST_OBS];
+  if ((n0 + ST_OBS <= jb.rows) && (i0 + ST_FEAT <= jb.cols)) {
+    const double* xp = jb.X + n0 * jb.ldx + i;
+#pragma unroll
+    for (int q = 0; q < ST_OBS; ++q) xv[q] = xp[q * jb.ldx];
+#pragma unroll
+    for (int q = 0; q < ST_OBS; ++q) xv[q] *= jb.sq[n0 + q];
+  } else {
+#pragma unroll
+    for (int q = 0; q < ST_OBS; ++q) {
+      const long n = n0 + q;
+      xv[q] = (n < jb.rows && live) ? jb.X[n * jb.ldx + i] * jb.sq[n] : 0.0;   // |x sq| < 2^e (same products as colmax)
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < ST_OBS / 16; ++h) {
+    Fixed4 f[4];
+#pragma unroll
+    for (int g4 = 0; g4 < 4; ++g4)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if constexpr (INTEGER)     // (the product with sqrt(s_n) above is the one FP64 instruction per element left)
+          fixed4_set_bits(f[g4], j, (unsigned long long)__double_as_longlong(xv[16 * h + 4 * g4 + j]), e + 1078 - 8 * S,
+                          digit_bias64(S));
+        else
+          fixed4_set(f[g4], j, xv[16 * h + 4 * g4 + j] * up * up2, bias);
+      }
+    if (live && n0 + 16 * h < jb.rows) {
+      int8_t* o = jb.out + (long)i * jb.ldo + n0 + 16 * h;
+#pragma unroll
+      for (int sl = 0; sl < S; ++sl) {
+        constexpr int NLO = INTEGER ? 4 : 3;
+        uint4 w;
+        w.x = fixed4_digits<S, NLO>(f[0], sl); w.y = fixed4_digits<S, NLO>(f[1], sl);
+        w.z = fixed4_digits<S, NLO>(f[2], sl); w.w = fixed4_digits<S, NLO>(f[3], sl);
+        *reinterpret_cast<uint4*>(o + (long)sl * jb.slice_stride) = w;
+      }
+    }
+  }
+}
+
+// CTA steps (feature blocks fastest: a wave reads whole rows of X), `nw` warps of which this one is `w`
+template <int S, bool INTEGER>
+__device__ __forceinline__ void slice_t_job(const SliceJob& jb, long cta, long nctas, int w, int nw, int lane) {
+  const long span = (long)ST_OBS * nw;
+  const long steps_x = (jb.rows + span - 1) / span;
+  const int tiles_y = (jb.cols + ST_FEAT - 1) / ST_FEAT;
+  for (long t = cta; t < steps_x * tiles_y; t += nctas) {
+    const long n0 = (t / tiles_y) * span + (long)w * ST_OBS;
+    if (n0 < jb.rows) slice_t_tile<S, INTEGER>(jb, n0, (int)(t % tiles_y) * ST_FEAT, lane, t < tiles_y && w == 0);
+  }
 }
 
 // Exact INT64 -> FP64 for |u| < 2^51 without a conversion instruction.
@@ -394,7 +526,7 @@ ogemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       // awaited: a global load behind the TMEM wait would sit on the critical path of every strip)
       const int ccol = n0 + chalf * (OBN / 2) + lane;
       const double cs_lane = (a.colscale && ccol < a.N) ? a.colscale[ccol] : 1.0;
-      mbar_wait_(tfull, tph);
+      mbar_wait_relaxed_(tfull, tph, a.epi_sleep_ns);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(chalf * (OBN / 2));
 #pragma unroll 1
@@ -453,8 +585,12 @@ ogemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     const int cw = warp;
     const bool vec = (a.next.ldx % 2 == 0) && (reinterpret_cast<uintptr_t>(a.next.X) % 16 == 0);
     const long long t_begin = clock64();
-    for (long r = (long)blockIdx.x * O_CONV_WARPS + cw; r < a.next.rows; r += (long)gridDim.x * O_CONV_WARPS)
-      slice_one_row<S, 8>(a.next, r, lane, vec);
+    if (a.next.colmax) {
+      slice_t_job<S, true>(a.next, blockIdx.x, gridDim.x, cw, O_CONV_WARPS, lane);
+    } else {
+      for (long r = (long)blockIdx.x * O_CONV_WARPS + cw; r < a.next.rows; r += (long)gridDim.x * O_CONV_WARPS)
+        slice_one_row<S, 8, true>(a.next, r, lane, vec);
+    }
     if (a.timing && lane == 0) {
       atomicAdd(a.timing + 5, (unsigned long long)(clock64() - t_begin));
       atomicAdd(a.timing + 6, 1ULL);
@@ -521,74 +657,9 @@ __global__ void __launch_bounds__(256) ozaki_colmax_kernel(const double* __restr
   }
 }
 
-// Tile of 128 observations x 32 features per CTA: coalesced FP64 reads along the features, digits
-// staged in shared memory ([slice][feature][observation], pitch 132 bytes: conflict free for the
-// feature-per-lane stores), 128-byte coalesced stores along the observations.
-constexpr int ST_OBS = 128, ST_FEAT = 32, ST_PITCH = ST_OBS + 4;
-template <int S>
-__global__ void __launch_bounds__(256) ozaki_slice_t_kernel(const double* __restrict__ X, long ldx, long rows, int cols,
-                                                            const double* __restrict__ sq,
-                                                            const unsigned long long* __restrict__ colmax,
-                                                            int8_t* __restrict__ out, long ldo, long slice_stride,
-                                                            double* __restrict__ scale_out) {
-  __shared__ __align__(16) int8_t sm[S * ST_FEAT * ST_PITCH];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long tiles_x = (rows + ST_OBS - 1) / ST_OBS;
-  const int tiles_y = (cols + ST_FEAT - 1) / ST_FEAT;
-  constexpr uint32_t bias = digit_bias_hi(S);
-  for (long tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
-    const long n0 = (tile / tiles_y) * ST_OBS;          // feature blocks fastest: a CTA wave reads whole rows of X
-    const int i0 = (int)(tile % tiles_y) * ST_FEAT;
-    const int i = i0 + lane;
-    int e = 0;
-    if (i < cols) {
-      const double m = __longlong_as_double((long long)colmax[i]);
-      const bool finite = m <= 1.7976931348623157e308;
-      if (finite && m > 0.0) (void)frexp(m, &e);
-      if (n0 == 0 && warp == 0) scale_out[i] = finite ? ldexp(1.0, e) : m;   // NaN scale: row and column i of H become NaN
-    }
-    const double up = ldexp(1.0, 8 * S - 2 - e);
-    // a warp takes 16 consecutive observations of the tile (lane = feature: 256-byte coalesced reads), all 16 loads
-    // in flight at once; the digits of four observations of one slice pack into one 32-bit shared-memory store
-    const int rbase = 16 * warp;
-    double xv[16];
-    const bool full = (n0 + ST_OBS <= rows) && (i0 + ST_FEAT <= cols);
-    if (full) {
-      const double* xp = X + (n0 + rbase) * ldx + i;
-#pragma unroll
-      for (int q = 0; q < 16; ++q) xv[q] = xp[q * ldx];
-#pragma unroll
-      for (int q = 0; q < 16; ++q) xv[q] *= sq[n0 + rbase + q];
-    } else {
-#pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const long n = n0 + rbase + q;
-        xv[q] = (n < rows && i < cols) ? X[n * ldx + i] * sq[n] : 0.0;     // |x sq| < 2^e (same products as colmax)
-      }
-    }
-#pragma unroll
-    for (int g4 = 0; g4 < 4; ++g4) {
-      Fixed4 f;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) fixed4_set(f, j, xv[4 * g4 + j] * up, bias);
-#pragma unroll
-      for (int sl = 0; sl < S; ++sl)
-        *reinterpret_cast<uint32_t*>(sm + (sl * ST_FEAT + lane) * ST_PITCH + rbase + 4 * g4) = fixed4_digits<S>(f, sl);
-    }
-    __syncthreads();
-    // (slice, feature) rows of 128 bytes: one warp per row, 4 bytes per lane
-    if (n0 + 4 * lane < ldo) {
-#pragma unroll 4
-      for (int row = warp; row < S * ST_FEAT; row += 8) {
-        const int sl = row / ST_FEAT, f = row % ST_FEAT;
-        if (i0 + f < cols) {
-          const uint32_t v = *reinterpret_cast<const uint32_t*>(sm + row * ST_PITCH + 4 * lane);
-          *reinterpret_cast<uint32_t*>(out + (long)sl * slice_stride + (long)(i0 + f) * ldo + n0 + 4 * lane) = v;
-        }
-      }
-    }
-    __syncthreads();
-  }
+template <int S, bool INTEGER = false>
+__global__ void __launch_bounds__(32 * ST_GROUP) ozaki_slice_t_kernel(const SliceJob jb) {
+  slice_t_job<S, INTEGER>(jb, blockIdx.x, gridDim.x, threadIdx.x >> 5, ST_GROUP, threadIdx.x & 31);
 }
 
 // H = sum of the split-K partial buffers over the lower triangle, mirrored (exactly symmetric).
@@ -635,6 +706,15 @@ bool ozaki_fuse_slicing() {
   return on;
 }
 
+// VT_EPI_SLEEP_NS: nanoseconds the waiting epilogue warps sleep between polls (A/B measurements; 0 = spin).
+unsigned epilogue_sleep_ns() {
+  static const unsigned ns = [] {
+    const char* e = getenv("VT_EPI_SLEEP_NS");
+    return e ? (unsigned)atoi(e) : 0u;
+  }();
+  return ns;
+}
+
 // VT_OGEMM_STACK=0 selects the one-product-per-instruction issue loop (N = 64) for A/B measurements.
 bool ogemm_stacked() {
   static const bool on = [] {
@@ -662,7 +742,8 @@ int launch_s(const CUtensorMap& mA, const CUtensorMap& mB, const OKernelArgs& a,
   VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, OCfg<S>::SMEM_BYTES));
   VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   const long slots = num_sms();
-  const int grid = (int)(a.units < slots ? a.units : slots);
+  // CTAs without a unit still run their share of the slicing job
+  const int grid = (int)((a.units < slots && !a.next.X) ? a.units : slots);
   kern<<<grid, O_THREADS, OCfg<S>::SMEM_BYTES, stream>>>(mA, mB, a);
   VT_LAUNCH_CHECK();
   return VT_OK;
@@ -732,7 +813,7 @@ long ozaki_chunk_rows(long N, int D, int nslices) {
 unsigned long long* ogemm_timing_buffer_public() { return ogemm_timing_buffer(); }
 
 int ozaki_slice(const double* X, long ldx, long rows, int cols, int8_t* out, long ldo, long slice_stride, int nslices,
-                double* scale_out, const double* fold, cudaStream_t stream) {
+                double* scale_out, const double* fold, cudaStream_t stream, int integer_variant) {
   VT_REQUIRE(X && out && scale_out, "ozaki_slice: null pointer");
   VT_REQUIRE(rows >= 0 && cols >= 1 && ldx >= cols && ldo >= cols && ldo % 16 == 0, "ozaki_slice: bad shape");
   VT_REQUIRE(nslices >= OZAKI_MIN_SLICES && nslices <= OZAKI_MAX_SLICES && slice_stride >= rows * ldo && slice_stride % 16 == 0,
@@ -746,7 +827,17 @@ int ozaki_slice(const double* X, long ldx, long rows, int cols, int8_t* out, lon
   const long cap = (long)num_sms() * (ozaki_overlap() ? 2 : 8);
   if (blocks > cap) blocks = cap;
   const int rc = cols <= 1024 ? (cols + 127) / 128 : 0;        // rows of up to 1024 elements stay in registers
-  const SliceJob jb{X, ldx, rows, cols, out, ldo, slice_stride, scale_out, fold};
+  const SliceJob jb{X, ldx, rows, cols, out, ldo, slice_stride, scale_out, fold, nullptr, nullptr};
+  if (integer_variant) {       // the converter warps' instruction sequence as a kernel of its own (tests)
+    VT_REQUIRE(cols <= 1024, "ozaki_slice: the integer variant takes rows of at most 1024 elements");
+    switch (nslices) {
+      case 5: ozaki_slice_kernel<5, 8, true><<<(unsigned)blocks, bt, 0, stream>>>(jb); break;
+      case 6: ozaki_slice_kernel<6, 8, true><<<(unsigned)blocks, bt, 0, stream>>>(jb); break;
+      default: ozaki_slice_kernel<7, 8, true><<<(unsigned)blocks, bt, 0, stream>>>(jb); break;
+    }
+    VT_LAUNCH_CHECK();
+    return VT_OK;
+  }
 #define VT_SLICE_CASE(SS, RR) ozaki_slice_kernel<SS, RR><<<(unsigned)blocks, bt, 0, stream>>>(jb)
 #define VT_SLICE_S(SS)                                                           \
   switch (rc) {                                                                  \
@@ -763,6 +854,30 @@ int ozaki_slice(const double* X, long ldx, long rows, int cols, int8_t* out, lon
   }
 #undef VT_SLICE_S
 #undef VT_SLICE_CASE
+  VT_LAUNCH_CHECK();
+  return VT_OK;
+}
+
+// Transposed digits out[s][feature][observation] of sq_n x_ni (the Hessian's operand) as a launch of its own.
+int ozaki_slice_t(const double* X, long ldx, long rows, int cols, const double* sq, const unsigned long long* colmax,
+                  int8_t* out, long ldo, long slice_stride, int nslices, double* scale_out, int integer_variant,
+                  int max_ctas, cudaStream_t stream) {
+  VT_REQUIRE(X && sq && colmax && out && scale_out, "ozaki_slice_t: null pointer");
+  VT_REQUIRE(rows >= 1 && cols >= 1 && ldx >= cols && ldo >= rows && ldo % 16 == 0 && slice_stride >= (long)cols * ldo &&
+             slice_stride % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0, "ozaki_slice_t: bad layout");
+  VT_REQUIRE(nslices >= OZAKI_MIN_SLICES && nslices <= OZAKI_MAX_SLICES, "ozaki_slice_t: 5, 6 or 7 slices");
+  const SliceJob jb{X, ldx, rows, cols, out, ldo, slice_stride, scale_out, nullptr, sq, colmax};
+  const long steps = ((rows + ST_OBS * ST_GROUP - 1) / (ST_OBS * ST_GROUP)) * ((cols + ST_FEAT - 1) / ST_FEAT);
+  const unsigned grid = (unsigned)(steps < max_ctas ? steps : max_ctas);
+#define VT_SLICE_T(SS)                                                                              \
+  if (integer_variant) ozaki_slice_t_kernel<SS, true><<<grid, 32 * ST_GROUP, 0, stream>>>(jb);     \
+  else ozaki_slice_t_kernel<SS, false><<<grid, 32 * ST_GROUP, 0, stream>>>(jb)
+  switch (nslices) {
+    case 5: VT_SLICE_T(5); break;
+    case 6: VT_SLICE_T(6); break;
+    default: VT_SLICE_T(7); break;
+  }
+#undef VT_SLICE_T
   VT_LAUNCH_CHECK();
   return VT_OK;
 }
@@ -814,8 +929,11 @@ int ogemm_launch_opts(int M, int N, int K, const int8_t* A, long lda, long a_sli
   a.rowscale = rowscale; a.colscale = colscale;
   a.c_vec = (ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(C) % 32 == 0) && (o.part_stride % 4 == 0);
   a.next = o.next;
-  if (a.next.X) VT_REQUIRE(a.next.cols <= 1024 && a.next.ldo % 16 == 0, "ogemm: in-kernel slicing takes rows of at most 1024 elements");
+  if (a.next.X)
+    VT_REQUIRE((a.next.colmax || a.next.cols <= 1024) && a.next.ldo % 16 == 0,
+               "ogemm: in-kernel slicing takes rows of at most 1024 elements");
   a.timing = ogemm_timing_buffer();
+  a.epi_sleep_ns = epilogue_sleep_ns();
   const bool stk = ogemm_stacked();
   switch (nslices) {
     case 5: return stk ? launch_s<5, true>(mA, mB, a, stream) : launch_s<5, false>(mA, mB, a, stream);
@@ -1010,7 +1128,7 @@ int ij_apply_ozaki(const double* Hinv, long ldh, const double* X, long ldx, long
     const long n0 = r0 + ch;
     if (fuse && n0 < N) {
       const long nrows = (N - n0 < ch) ? N - n0 : ch;
-      o.next = SliceJob{X + n0 * ldx, ldx, nrows, D, Bs[b ^ 1], ld, ch * ld, tau[b ^ 1], resid + n0};
+      o.next = SliceJob{X + n0 * ldx, ldx, nrows, D, Bs[b ^ 1], ld, ch * ld, tau[b ^ 1], resid + n0, nullptr, nullptr};
     }
     st = ogemm_launch_opts(D, (int)rows, D, As, ld, (long)D * ld, Bs[b], ld, ch * ld, nslices, -1.0, sigma, tau[b], S + r0, lds,
                            o, stream);
@@ -1034,7 +1152,7 @@ SyrkPlan syrk_plan(long N, int D, int nslices) {
   for (int tm = 0; tm < tiles_m; ++tm) ntiles += o_lower_cols(tm, tiles_n);
   int parts = (int)(num_sms() / ntiles);
   if (parts < 1) parts = 1;
-  if (parts > 8) parts = 8;
+  if (parts > 16) parts = 16;
   p.parts = parts;
   long chunk = (long)parts * OZAKI_MAX_K;                       // every part accumulates at most 16384 observations in INT32
   const size_t budget = (size_t)320 << 20;                      // all slices of one chunk
@@ -1107,20 +1225,24 @@ int syrk_ozaki(const double* X, long ldx, long N, int D, const double* s, double
     VT_CUDA(cudaStreamWaitEvent(L->side, L->fork, 0));
     slicer = L->side;
   }
+  // Chunk c + 1 is sliced by the converter warps of the GEMM of chunk c (VT_OZAKI_FUSE=0: a slicing launch per chunk,
+  // which cannot share an SM with the GEMM's 210 KB of shared memory and so runs between the GEMMs).
+  const bool fuse = !overlap && ozaki_fuse_slicing();
+  auto job = [&](long r0, int b) {
+    const long rows = (N - r0 < p.chunk) ? N - r0 : p.chunk;
+    return SliceJob{X + r0 * ldx, ldx, rows, D, Xs[b], p.ld, slice_stride, sigma, nullptr, sq_use + r0, cmax_use};
+  };
   long c = 0;
   for (long r0 = 0; r0 < N; r0 += p.chunk, ++c) {
     const int b = (int)(c & 1);
     const long rows = (N - r0 < p.chunk) ? N - r0 : p.chunk;
     if (overlap && c >= 2) VT_CUDA(cudaStreamWaitEvent(L->side, L->consumed[b], 0));
-    const long tiles = ((rows + ST_OBS - 1) / ST_OBS) * ((D + ST_FEAT - 1) / ST_FEAT);
-    const long cap = (long)num_sms() * (overlap ? 1 : 6);
-    const unsigned tgrid = (unsigned)(tiles < cap ? tiles : cap);
-    switch (nslices) {
-      case 5: ozaki_slice_t_kernel<5><<<tgrid, 256, 0, slicer>>>(X + r0 * ldx, ldx, rows, D, sq_use + r0, cmax_use, Xs[b], p.ld, slice_stride, sigma); break;
-      case 6: ozaki_slice_t_kernel<6><<<tgrid, 256, 0, slicer>>>(X + r0 * ldx, ldx, rows, D, sq_use + r0, cmax_use, Xs[b], p.ld, slice_stride, sigma); break;
-      default: ozaki_slice_t_kernel<7><<<tgrid, 256, 0, slicer>>>(X + r0 * ldx, ldx, rows, D, sq_use + r0, cmax_use, Xs[b], p.ld, slice_stride, sigma); break;
+    if (!fuse || c == 0) {
+      const SliceJob jb = job(r0, b);
+      st = ozaki_slice_t(jb.X, ldx, jb.rows, D, jb.sq, cmax_use, Xs[b], p.ld, slice_stride, nslices, sigma, 0,
+                         num_sms() * (overlap ? 1 : 6), slicer);
+      if (st != VT_OK) return st;
     }
-    VT_LAUNCH_CHECK();
     if (overlap) {
       VT_CUDA(cudaEventRecord(L->ready[b], L->side));
       VT_CUDA(cudaStreamWaitEvent(stream, L->ready[b], 0));
@@ -1130,6 +1252,7 @@ int syrk_ozaki(const double* X, long ldx, long N, int D, const double* s, double
     o.parts = p.parts;
     o.accumulate = 1;
     o.part_stride = (long)D * D;
+    if (fuse && r0 + p.chunk < N) o.next = job(r0 + p.chunk, b ^ 1);
     st = ogemm_launch_opts(D, D, (int)rows, Xs[b], p.ld, slice_stride, Xs[b], p.ld, slice_stride, nslices, 1.0, sigma, sigma,
                            P, D, o, stream);
     if (st != VT_OK) return st;

@@ -535,6 +535,13 @@ ogemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
 #pragma unroll
         for (int g = 0; g < S; ++g) tmem_ld8(taddr + (uint32_t)(g * OBN + c), v[g]);
         tmem_wait_ld();
+        if (c + 8 == OBN / 2) {
+          // the last loads have landed: the accumulators go back to the MMA warp now, and the arithmetic and the
+          // stores of this final chunk overlap the next tile's first MMAs
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_(tempty);
+        }
         double out[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -572,9 +579,6 @@ ogemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_(tempty);
       tph ^= 1u;
     }
   } else if (a.next.X != nullptr) {

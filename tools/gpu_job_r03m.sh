@@ -1,0 +1,3 @@
+set -x
+python tools/chol_probe.py | cut -c1-330
+python -m pytest tests/test_gpu_solver.py tests/test_gpu_lrcov.py tests/test_gpu_ij.py -q -x 2>&1 | tail -2

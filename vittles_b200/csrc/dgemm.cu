@@ -438,6 +438,8 @@ int gemm_launch(GemmParams p, cudaStream_t stream) {
     VT_REQUIRE(p.workspace && p.workspace_bytes >= (size_t)p.ntiles * p.parts * p.tile * p.tile * 8,
                "gemm: split-K workspace too small (%zu bytes for %d parts x %d tiles)", p.workspace_bytes,
                p.parts, p.ntiles);
+  if (p.parts > 1)
+    VT_REQUIRE(reinterpret_cast<uintptr_t>(p.workspace) % 16 == 0, "gemm: the split-K workspace must be 16-byte aligned");
   const long units = (long)p.ntiles * p.parts;
   const long slots = (long)num_sms() * ctas_per_sm(p.tile);
   long cap = slots - (long)p.spare_sms * ctas_per_sm(p.tile);

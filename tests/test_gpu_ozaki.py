@@ -110,6 +110,12 @@ def test_transposed_slicer_variants_match_the_cpu_model(vt, S, shape):
     assert np.array_equal(d_int[:, :, :N].cpu().numpy(), d_ref)
     assert np.array_equal(sc_int.cpu().numpy(), sc_ref)
     assert bool((d_int[:, :, N:] == 0).all())
+    # unweighted (the Schur complement Z^T Z of the block-arrow solver): no multiplication at all
+    d_fp, sc_fp = vt.ops.ozaki_slice_t(X, None, S)
+    d_int, sc_int = vt.ops.ozaki_slice_t(X, None, S, integer_variant=True)
+    d_ref, sc_ref = slicing.slice_rows(X.T.contiguous().cpu().numpy(), S)
+    assert torch.equal(sc_fp, sc_int) and torch.equal(d_fp, d_int)
+    assert np.array_equal(d_int[:, :, :N].cpu().numpy(), d_ref) and np.array_equal(sc_int.cpu().numpy(), sc_ref)
 
 
 def test_extreme_digits_do_not_overflow_int32(vt):

@@ -30,7 +30,9 @@ def main():
     for N, D in zip(args[0::2], args[1::2]):
         X = ops.synth_design(7, 0, N, D, dev)
         s = torch.rand(N, device=dev, dtype=torch.float64, generator=torch.Generator(device=dev).manual_seed(N + D))
-        row = {'N': N, 'D': D, 'fuse': os.environ.get('VT_OZAKI_FUSE', '1')}
+        if os.environ.get('VT_PROBE_UNWEIGHTED') == '1':       # X^T X (the Schur complement of config 3)
+            s = None
+        row = {'N': N, 'D': D, 'fuse': os.environ.get('VT_OZAKI_FUSE', '1'), 'weighted': s is not None}
         for prec in ('f64_ozaki', 'f64'):
             ms, H = timed(lambda: ops.syrk_weighted(X, s, precision=prec), 3)
             row[prec + '_ms'] = ms

@@ -134,6 +134,12 @@ __device__ __forceinline__ void fixed4_set(Fixed4& f, int j, double t, uint32_t 
 // minus one plus the bit that would become the last (n >= 0 because |x| < 2^e, except in a row whose maximum is
 // subnormal, where the shift goes left).  Here lo holds the positions 0..3 and hi the positions 4..S-1 (NLO = 4 in
 // fixed4_digits).
+// frexp exponent of a finite non-negative double given by its bit pattern (0 for zero), in integer instructions
+__device__ __forceinline__ int frexp_exponent_bits(unsigned long long mb) {
+  const int eb = (int)(mb >> 52);
+  if (eb) return eb - 1022;
+  return mb ? -1010 - __clzll((long long)mb) : 0;      // subnormal: highest set bit p = 63 - clz  ->  p - 1073
+}
 __host__ __device__ constexpr unsigned long long digit_bias64(int nslices) { return 0x8080808080808080ULL >> (8 * (8 - nslices)); }
 __device__ __forceinline__ void fixed4_set_bits(Fixed4& f, int j, unsigned long long bits, int k2, unsigned long long bias64) {
   const int eb = (int)((bits >> 52) & 0x7ffULL);
@@ -230,7 +236,11 @@ __device__ __forceinline__ void slice_one_row(const SliceJob& jb, long r, int la
     finite = __all_sync(0xffffffffu, finite);
   }
   int e = 0;
-  if (finite && m > 0.0) (void)frexp(m, &e);         // m = f 2^e, f in [0.5, 1)  ->  |x| 2^-e < 1
+  if constexpr (INTEGER) {
+    if (finite) e = frexp_exponent_bits((unsigned long long)__double_as_longlong(m));
+  } else {
+    if (finite && m > 0.0) (void)frexp(m, &e);       // m = f 2^e, f in [0.5, 1)  ->  |x| 2^-e < 1
+  }
   // |x * up * up2| <= 2^(8S-2); the power of two goes in two factors because rows below ~1e-290 need more than 2^1023
   const int sh = 8 * S - 2 - e;
   const double up = ldexp(1.0, sh > 1000 ? 1000 : sh), up2 = ldexp(1.0, sh > 1000 ? sh - 1000 : 0);
@@ -295,9 +305,14 @@ __device__ __forceinline__ void slice_t_tile(const SliceJob& jb, long n0, int i0
   const bool live = i < jb.cols;
   int e = 0;
   if (live) {
-    const double m = __longlong_as_double((long long)jb.colmax[i]);
-    const bool finite = m <= 1.7976931348623157e308;
-    if (finite && m > 0.0) (void)frexp(m, &e);
+    const unsigned long long mb = jb.colmax[i];
+    const double m = __longlong_as_double((long long)mb);
+    const bool finite = mb < 0x7ff0000000000000ULL;
+    if constexpr (INTEGER) {
+      if (finite) e = frexp_exponent_bits(mb);
+    } else {
+      if (finite && m > 0.0) (void)frexp(m, &e);
+    }
     if (first) jb.scale_out[i] = finite ? ldexp(1.0, e) : m;   // NaN scale: row and column i of H become NaN
   }
   const int sh = 8 * S - 2 - e;
@@ -307,13 +322,16 @@ __device__ __forceinline__ void slice_t_tile(const SliceJob& jb, long n0, int i0
     const double* xp = jb.X + n0 * jb.ldx + i;
 #pragma unroll
     for (int q = 0; q < ST_OBS; ++q) xv[q] = xp[q * jb.ldx];
+    if (jb.sq) {                  // (unweighted: no FP64 instruction per element at all)
 #pragma unroll
-    for (int q = 0; q < ST_OBS; ++q) xv[q] *= jb.sq[n0 + q];
+      for (int q = 0; q < ST_OBS; ++q) xv[q] *= jb.sq[n0 + q];
+    }
   } else {
 #pragma unroll
     for (int q = 0; q < ST_OBS; ++q) {
       const long n = n0 + q;
-      xv[q] = (n < jb.rows && live) ? jb.X[n * jb.ldx + i] * jb.sq[n] : 0.0;   // |x sq| < 2^e (same products as colmax)
+      xv[q] = (n < jb.rows && live) ? jb.X[n * jb.ldx + i] : 0.0;
+      if (jb.sq && n < jb.rows) xv[q] *= jb.sq[n];                      // |x sq| < 2^e (same products as colmax)
     }
   }
 #pragma unroll
@@ -635,7 +653,7 @@ __global__ void __launch_bounds__(256) ozaki_colmax_kernel(const double* __restr
           v = (sv == sv) ? sqrt(fmax(sv, 0.0)) : sv;         // a NaN weight stays NaN (fmax would drop it)
         }
         sq[threadIdx.x] = v;
-        if (cbase == 0) sq_out[r_begin + threadIdx.x] = v;
+        if (cbase == 0 && sq_out) sq_out[r_begin + threadIdx.x] = v;
       }
       __syncthreads();
 #pragma unroll
@@ -866,7 +884,7 @@ int ozaki_slice(const double* X, long ldx, long rows, int cols, int8_t* out, lon
 int ozaki_slice_t(const double* X, long ldx, long rows, int cols, const double* sq, const unsigned long long* colmax,
                   int8_t* out, long ldo, long slice_stride, int nslices, double* scale_out, int integer_variant,
                   int max_ctas, cudaStream_t stream) {
-  VT_REQUIRE(X && sq && colmax && out && scale_out, "ozaki_slice_t: null pointer");
+  VT_REQUIRE(X && colmax && out && scale_out, "ozaki_slice_t: null pointer");      // sq == nullptr: unweighted
   VT_REQUIRE(rows >= 1 && cols >= 1 && ldx >= cols && ldo >= rows && ldo % 16 == 0 && slice_stride >= (long)cols * ldo &&
              slice_stride % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0, "ozaki_slice_t: bad layout");
   VT_REQUIRE(nslices >= OZAKI_MIN_SLICES && nslices <= OZAKI_MAX_SLICES, "ozaki_slice_t: 5, 6 or 7 slices");
@@ -1214,7 +1232,8 @@ int syrk_ozaki(const double* X, long ldx, long N, int D, const double* s, double
     VT_CUDA(cudaMemsetAsync(cmax, 0, (size_t)D * 8, stream));
     long nsteps = (N + 31) / 32;
     const long cap = (long)num_sms() * 8;
-    ozaki_colmax_kernel<<<(unsigned)(nsteps < cap ? nsteps : cap), 256, 0, stream>>>(X, ldx, N, D, s, sq, cmax);
+    if (!s) sq_use = nullptr;            // unweighted: the slicers skip the multiplication
+    ozaki_colmax_kernel<<<(unsigned)(nsteps < cap ? nsteps : cap), 256, 0, stream>>>(X, ldx, N, D, s, s ? sq : nullptr, cmax);
     VT_LAUNCH_CHECK();
   }
   VT_CUDA(cudaMemsetAsync(P, 0, (size_t)p.parts * D * D * 8, stream));      // every chunk (and part) accumulates
@@ -1234,7 +1253,7 @@ int syrk_ozaki(const double* X, long ldx, long N, int D, const double* s, double
   const bool fuse = !overlap && ozaki_fuse_slicing();
   auto job = [&](long r0, int b) {
     const long rows = (N - r0 < p.chunk) ? N - r0 : p.chunk;
-    return SliceJob{X + r0 * ldx, ldx, rows, D, Xs[b], p.ld, slice_stride, sigma, nullptr, sq_use + r0, cmax_use};
+    return SliceJob{X + r0 * ldx, ldx, rows, D, Xs[b], p.ld, slice_stride, sigma, nullptr, sq_use ? sq_use + r0 : nullptr, cmax_use};
   };
   long c = 0;
   for (long r0 = 0; r0 < N; r0 += p.chunk, ++c) {

@@ -190,14 +190,16 @@ def ozaki_slice(X, nslices=OZAKI_SLICES, fold=None, integer_variant=False):
 
 def ozaki_slice_t(X, sq, nslices=OZAKI_SLICES, integer_variant=False):
     """The Hessian's operand: (digits (nslices, cols, ld) int8, scale (cols,) float64) of
-    sq[n] * X[n, i], transposed (observations contiguous), one power-of-two scale per feature."""
+    sq[n] * X[n, i] (sq None: of X[n, i]), transposed (observations contiguous), one power-of-two scale per feature."""
     lib = _cabi.require_cuda()
     _mat(X, 'X')
     rows, cols = X.shape
-    _f64(sq, 'sq')
-    if sq.numel() != rows:
-        raise ValueError('sq must have one entry per row of X')
-    cmax = (X * sq[:, None]).abs().amax(dim=0).contiguous().view(torch.int64)    # bit patterns of the maxima
+    if sq is not None:
+        _f64(sq, 'sq')
+        if sq.numel() != rows:
+            raise ValueError('sq must have one entry per row of X')
+    W = X if sq is None else X * sq[:, None]
+    cmax = W.abs().amax(dim=0).contiguous().view(torch.int64)                    # bit patterns of the maxima
     ld = (rows + 15) // 16 * 16
     out = torch.zeros((nslices, cols, ld), dtype=torch.int8, device=X.device)
     scale = torch.empty(cols, dtype=torch.float64, device=X.device)
@@ -262,7 +264,7 @@ def syrk_weighted(X, s=None, l2=0.0, out=None, precision='f64', colmax=None):
     N, D = X.shape
     precision = resolve_precision(precision, N, D, s)
     split = _split(precision)
-    if s is None and not split:
+    if s is None and not split and precision != 'f64_ozaki':      # (the INT8 engine takes "unweighted" as such)
         s = torch.ones(N, dtype=torch.float64, device=X.device)
     if s is not None:
         _f64(s, 's')

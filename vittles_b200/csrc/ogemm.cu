@@ -53,7 +53,6 @@ struct OKernelArgs {
   const double* colscale;
   int c_vec;
   SliceJob next;                // rows to slice during this launch (X == nullptr: none; cols <= 1024)
-  unsigned epi_sleep_ns;        // the epilogue warps poll for the accumulators this often (0: spin)
   unsigned long long* timing;   // development aid (VT_OGEMM_TIMING=1): clocks the MMA thread waits, summed over CTAs
 };
 
@@ -544,7 +543,7 @@ ogemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       // awaited: a global load behind the TMEM wait would sit on the critical path of every strip)
       const int ccol = n0 + chalf * (OBN / 2) + lane;
       const double cs_lane = (a.colscale && ccol < a.N) ? a.colscale[ccol] : 1.0;
-      mbar_wait_relaxed_(tfull, tph, a.epi_sleep_ns);
+      mbar_wait_(tfull, tph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(chalf * (OBN / 2));
 #pragma unroll 1
@@ -726,15 +725,6 @@ bool ozaki_fuse_slicing() {
     return !(e && e[0] == '0');
   }();
   return on;
-}
-
-// VT_EPI_SLEEP_NS: nanoseconds the waiting epilogue warps sleep between polls (A/B measurements; 0 = spin).
-unsigned epilogue_sleep_ns() {
-  static const unsigned ns = [] {
-    const char* e = getenv("VT_EPI_SLEEP_NS");
-    return e ? (unsigned)atoi(e) : 0u;
-  }();
-  return ns;
 }
 
 // VT_OGEMM_STACK=0 selects the one-product-per-instruction issue loop (N = 64) for A/B measurements.
@@ -955,7 +945,6 @@ int ogemm_launch_opts(int M, int N, int K, const int8_t* A, long lda, long a_sli
     VT_REQUIRE((a.next.colmax || a.next.cols <= 1024) && a.next.ldo % 16 == 0,
                "ogemm: in-kernel slicing takes rows of at most 1024 elements");
   a.timing = ogemm_timing_buffer();
-  a.epi_sleep_ns = epilogue_sleep_ns();
   const bool stk = ogemm_stacked();
   switch (nslices) {
     case 5: return stk ? launch_s<5, true>(mA, mB, a, stream) : launch_s<5, false>(mA, mB, a, stream);

@@ -38,16 +38,6 @@ __device__ __forceinline__ void mbar_wait_(uint32_t bar, uint32_t parity) {
     if (clock64() - t0 > SPIN_LIMIT_CLOCKS) __trap();
   }
 }
-// Wait of a warp that is NOT on the critical path: sleeps between the polls so that its spinning does not take
-// issue slots from the warps that share its scheduler.
-__device__ __forceinline__ void mbar_wait_relaxed_(uint32_t bar, uint32_t parity, unsigned sleep_ns) {
-  if (mbar_try_wait_(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait_(bar, parity)) {
-    if (sleep_ns) __nanosleep(sleep_ns);
-    if (clock64() - t0 > SPIN_LIMIT_CLOCKS) __trap();
-  }
-}
 __device__ __forceinline__ void fence_barrier_init_() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }

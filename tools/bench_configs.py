@@ -45,13 +45,15 @@ class Ctx:
         max over the ranks"""
         out = None
         for _ in range(warm):
-            out = fn()
+            out = None                     # drop the previous result first: its blocks go back to the caching allocator
+            out = fn()                     # and no cudaMalloc of a multi-GB result lands in the timed region
         torch.cuda.synchronize()
         if self.group is not None:
             dist.barrier(self.group)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for _ in range(reps):
+            out = None
             out = fn()
         b.record()
         torch.cuda.synchronize()

@@ -421,11 +421,13 @@ def main():
     if not args.no_e2e:
         try:
             room0 = host_headroom_bytes()
-            need0 = int(1.15 * 8.0 * n_loc * D * (world if world > 1 else 1))
+            need0 = world * pinned_cost(8 * n_loc * D) + host_reserve_bytes()
             if room0 is not None and room0 < need0:
-                raise MemoryError('host memory headroom {:.0f} GB < {:.0f} GB needed to stage the inputs'.format(
-                    room0 / 1e9, need0 / 1e9))
+                raise MemoryError('host memory headroom {:.0f} GB < {:.0f} GB needed to stage the inputs (pinned blocks '
+                                  'come in powers of two) and keep a reserve'.format(room0 / 1e9, need0 / 1e9))
+            memlog('before staging')
             host = stage_to_host(torch, X, y, theta)
+            memlog('inputs staged')
             # free every device-resident tensor of the resident phase: the e2e step brings its own
             obj.X = obj.y = obj = None
             del X, y, st, H, hinv, w
@@ -433,6 +435,7 @@ def main():
             ops.free_workspaces()
             torch.cuda.empty_cache()
             e2e = run_e2e(args, vt, torch, dist, dev, group, world, host)
+            memlog('after e2e')
             e2e['numa'] = numa_note
             e2e['host_memory_headroom_gb_before_staging'] = None if room0 is None else room0 / 1e9
         except Exception as exc:      # report, never hide
@@ -441,7 +444,7 @@ def main():
         if e2e.get('value') and not args.no_e2e_full:
             # the (D, N) result needs as much host memory again as the inputs already staged (all ranks of the node
             # together); without clear headroom the leg is skipped - an out-of-memory kill would take the whole line
-            need = int(1.3 * 8.0 * N * D)
+            need = world * pinned_cost(8 * n_loc * D) + host_reserve_bytes()
             room = host_headroom_bytes()
             ok = torch.tensor([1 if (room is None or room >= need) else 0], device=dev)
             if world > 1:
@@ -456,6 +459,7 @@ def main():
                             'skipped': 'host memory headroom {:.0f} GB < {:.0f} GB needed to hold the (D, N) result next '
                                        'to the staged inputs'.format((room or 0) / 1e9, need / 1e9)}
 
+    memlog('after e2e_full')
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = use_all_host_cores()
@@ -503,7 +507,9 @@ def main():
             torch.cuda.empty_cache()
             sys.path.insert(0, os.path.join(ROOT, 'tools'))
             import bench_configs
+            memlog('before configs')
             configs = bench_configs.run_all(dev, group, peak=peak_tflops)
+            memlog('after configs')
         except Exception as exc:              # report, never hide
             configs = {'error': repr(exc)[:300]}
 
@@ -622,6 +628,15 @@ def engine_row(prec, vt, ops, torch, dist, world, group, dev, X, y, theta, w, st
     return row
 
 
+def memlog(tag):
+    """VT_BENCH_MEMLOG=1: available host memory at the stations of the run, on stderr (every rank)."""
+    if os.environ.get('VT_BENCH_MEMLOG') != '1':
+        return
+    room = host_headroom_bytes()
+    print('[mem] rank {} {:<28s} available {:.1f} GB'.format(os.environ.get('RANK', '0'), tag, (room or 0) / 1e9),
+          file=sys.stderr, flush=True)
+
+
 def stage_to_host(torch, X, y, theta):
     """Pinned host copies of this rank's inputs (set-up for the e2e leg)."""
     n_loc, D = X.shape
@@ -633,6 +648,23 @@ def stage_to_host(torch, X, y, theta):
     w1 = torch.ones(n_loc, dtype=torch.float64)
     w1[::7] = 0.0
     return dict(X=X_host, y=y_host, w=w_host, w1=w1.pin_memory(), theta=theta.cpu().pin_memory())
+
+
+def pinned_cost(nbytes):
+    """What a pinned tensor of `nbytes` takes from the host: torch's caching host allocator hands out blocks whose
+    sizes are powers of two (82 GB of inputs occupy 128 GB; measured: 2 x 41 GB shards took 139 GB)."""
+    n = int(nbytes)
+    return 1 << max(n - 1, 1).bit_length()
+
+
+def host_reserve_bytes():
+    """Host memory that must stay free after a staging allocation (page cache, NCCL's shared segments, the driver's
+    own processes on the box): a tenth of the machine, at least 16 GB."""
+    try:
+        import psutil
+        return max(16 << 30, int(0.10 * psutil.virtual_memory().total))
+    except Exception:
+        return 32 << 30
 
 
 def host_headroom_bytes():

@@ -42,6 +42,13 @@ def to_host(t):
     if t.numel() * t.element_size() < PINNED_STAGING_MIN_BYTES:
         return t.cpu()
     src = t if t.is_contiguous() else t.contiguous()
+    # torch's caching host allocator hands out pinned blocks in powers of two (an 82 GB result would lock 128 GB):
+    # when that block would take most of what the host has left, go through the small staging buffers instead -
+    # an over-committed pinned allocation does not raise, it gets the process killed
+    nbytes = src.numel() * src.element_size()
+    avail = _host_available_bytes()
+    if avail is not None and (1 << max(nbytes - 1, 1).bit_length()) > 0.7 * avail:
+        return _to_host_staged(src)
     try:
         out = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
     except RuntimeError:
@@ -56,14 +63,18 @@ def to_host(t):
 STAGING_BYTES = 512 << 20
 
 
+def _host_available_bytes():
+    try:
+        import psutil
+        return int(psutil.virtual_memory().available)
+    except Exception:
+        return None
+
+
 def _to_host_staged(src):
     flat = src.reshape(-1)
     n = flat.numel()
-    try:
-        import psutil
-        avail = psutil.virtual_memory().available
-    except Exception:
-        avail = None
+    avail = _host_available_bytes()
     if avail is not None and n * src.element_size() > 0.9 * avail:
         raise MemoryError('the result ({:.1f} GB) does not fit in the available host memory ({:.1f} GB); keep it on the '
                           'device (pass CUDA tensors in, get CUDA tensors back)'.format(n * src.element_size() / 1e9, avail / 1e9))

@@ -212,3 +212,26 @@ def test_bench_reference_arm_prints_the_contract_line():
                            '--cpu-sample', '3000'], capture_output=True, text=True, env=dict(env, RANK='1', WORLD_SIZE='2'),
                           timeout=120)
     assert out2.returncode == 0 and out2.stdout.strip() == ''
+
+
+def test_bench_host_memory_accounting():
+    """The e2e legs of bench.py stage tens of GB in pinned host memory; their guards must count what torch's
+    caching host allocator really takes (powers of two) and keep a reserve - an over-committed pinned allocation
+    does not raise, it gets every rank killed (seen at 2 GPUs on a 251 GB host)."""
+    import importlib.util
+    import sys
+    spec = importlib.util.spec_from_file_location('bench_for_test', os.path.join(ROOT, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    argv = sys.argv
+    sys.argv = ['bench.py']
+    try:
+        spec.loader.exec_module(bench)
+    finally:
+        sys.argv = argv
+    GB = 1 << 30
+    assert bench.pinned_cost(82 * 10 ** 9) == 128 * GB           # the inputs of the headline config on one GPU
+    assert bench.pinned_cost(41 * 10 ** 9) == 64 * GB            # ... and per rank on two
+    assert bench.pinned_cost(64 * GB) == 64 * GB and bench.pinned_cost(64 * GB + 1) == 128 * GB
+    assert bench.host_reserve_bytes() >= 16 * GB
+    room = bench.host_headroom_bytes()
+    assert room is None or room > 0

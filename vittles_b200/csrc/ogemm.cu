@@ -95,9 +95,12 @@ __device__ __forceinline__ OUnit o_decode(const OKernelArgs& a, long u) {
 // ring; slice s of A meets slices t = 0 .. S-1-s of B, and product (s, t) goes to
 // accumulator s + t.  Every INT8 tile loaded is used by (S+1)/2 products on
 // average, which keeps the L2 -> shared-memory traffic at ~47 B/clk/SM at the
-// tensor peak.  Measured (ncu, S = 8): tensor pipe 90 % active at 65 clk per
-// 128x64x32 MMA - the N = 64 tile that the S accumulators force is bound by the
-// shared-memory operand reads (6 KB per MMA), not by L2 or by issue.
+// tensor peak.  The products of one A slice are issued as ONE stacked
+// instruction (see the MMA issuer below); measured (ncu, S = 7, r02): tensor
+// pipe 80 % active, sm__memory_throughput 77 % - 389 KB of shared-memory operand
+// reads plus 168 KB of TMA writes per k-block against 3.5 k clocks of MMA issue -
+// and the epilogue exposed for 11 % of the tile time (all 448 of 512 TMEM columns
+// hold accumulators).  DESIGN.md 3.1 has the numbers.
 // Balanced base-256 digits.  q = rint(x 2^(8S-2) / sigma) (|q| <= 2^(8S-2) <= 2^54) is written as
 // q = sum_p d_p 256^p with every d_p in [-128, 127]: with the bias B = sum_p 128 256^p the ordinary bytes e_p of
 // u = q + B are d_p + 128, i.e. the digits are the bytes of u ^ B.  An int8 digit then carries a full 8 bits
@@ -108,7 +111,8 @@ __device__ __forceinline__ OUnit o_decode(const OKernelArgs& a, long u) {
 // of `nslices`) of four values is packed with PRMT into one word (byte j = value j).
 // (oracle/slicing.py is the CPU model; tests/test_gpu_ozaki.py compares digit for digit.)
 struct Fixed4 {
-  uint32_t lo[4], hi[4];       // biased digits: positions 0..2 in bytes 0..2 of lo, positions 3..S-1 in the bytes of hi
+  uint32_t lo[4], hi[4];       // biased digits: positions 0..NLO-1 in the low bytes of lo, the rest in the bytes of hi
+                               // (NLO = 3 from fixed4_set, 4 from fixed4_set_bits)
 };
 // bias of the S - 3 digits kept in the high word
 __host__ __device__ constexpr uint32_t digit_bias_hi(int nslices) { return 0x80808080u >> (8 * (7 - nslices)); }

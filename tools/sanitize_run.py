@@ -43,6 +43,15 @@ for (N, D) in ((3001, 77), (90000, 1024), (70000, 515)):
 A = rnd(130, 333)
 B = rnd(70, 333)
 print('ogemm', rel(ops.ozaki_gemm(A, B), A @ B.T))
+# the converter warps' integer-only slicers as kernels of their own, ragged shapes, and an unweighted Hessian
+# whose later chunks are sliced inside the GEMM
+Xr = rnd(517, 333)
+print('int slicer', torch.equal(ops.ozaki_slice(Xr, 7)[0], ops.ozaki_slice(Xr, 7, integer_variant=True)[0]))
+sqr = torch.rand(517, device=dev, dtype=torch.float64, generator=g).sqrt()
+for sq_ in (sqr, None):
+    print('transposed slicers', torch.equal(ops.ozaki_slice_t(Xr, sq_, 7)[0], ops.ozaki_slice_t(Xr, sq_, 7, integer_variant=True)[0]))
+Xu = ops.synth_design(4, 0, 70001, 650, dev)
+print('syrk unweighted', rel(ops.syrk_weighted(Xu, None, precision='f64_ozaki'), ops.syrk_weighted(Xu, None)))
 # batched CG with a Jacobi preconditioner
 d = 96
 a = rnd(d, d + 4)
@@ -67,7 +76,7 @@ for K in (1, 2, 40):
     b = rnd(dd, K)
     print('arrow', K, rel(vt.solver_lib.get_cholesky_solver(h)(b), torch.linalg.solve(dense, b)))
 # dense factor / solves crossing the 128 / 256 / 512 blockings
-for D, K in ((300, 37), (1100, 64), (1100, 3)):
+for D, K in ((300, 37), (1100, 64), (1100, 3), (1300, 1400)):
     a = rnd(D, D + 8)
     Hd = a @ a.T / D + torch.eye(D, device=dev, dtype=torch.float64)
     b = rnd(D, K)

@@ -385,12 +385,17 @@ def main():
     if args.engine_rows_only or (want_rows and world > 1):
         import gc
         engine_rows = {}
-        for prec in (('f64',) if engine == 'f64_ozaki' else ('f64_ozaki',)) + ('tf32x3', 'tf32'):
+        for prec in (('f64',) if engine == 'f64_ozaki' else ('f64_ozaki',)) + ('f64_ozaki_s6', 'tf32x3', 'tf32'):
+            slices0 = ops.OZAKI_SLICES
             try:
-                engine_rows[prec] = engine_row(prec, vt, ops, torch, dist, world, group, dev, X, y, theta, w, st, hinv,
-                                               idx, S_cols64, N, D, n_loc, reps, timed)
+                if prec == 'f64_ozaki_s6':    # the same engine with six digits per operand (46 bits, 21 digit products)
+                    ops.OZAKI_SLICES = 6
+                engine_rows[prec] = engine_row(prec.replace('_s6', ''), vt, ops, torch, dist, world, group, dev, X, y, theta,
+                                               w, st, hinv, idx, S_cols64, N, D, n_loc, reps, timed, note_key=prec)
             except Exception as exc:          # report, never hide
                 engine_rows[prec] = {'error': repr(exc)[:300]}
+            finally:
+                ops.OZAKI_SLICES = slices0
             gc.collect()
             torch.cuda.empty_cache()
         if args.engine_rows_only:
@@ -592,6 +597,8 @@ ENGINE_NOTES = {
     'f64_ozaki': ('both contractions on tcgen05.mma.kind::i8: 7 balanced base-256 slices per operand (54 bits), 28 exact '
                   'INT8 products, INT32 accumulators in TMEM, FP64 recombination; statistics, Cholesky and inverse in '
                   'FP64; held to the same rtol 1e-8 bar as the FP64 DMMA path'),
+    'f64_ozaki_s6': ('the INT8 slicing engine with 6 slices per operand (46 bits, 21 exact digit products; VT_OZAKI_SLICES=6): '
+                     'still inside the rtol 1e-8 bar, about two digits less than the 7-slice default'),
     'tf32x3': 'both contractions on tcgen05.mma.kind::tf32 with a three-term hi/lo split; the rest in FP64',
     'tf32': 'both contractions on tcgen05.mma.kind::tf32 (TMEM accumulators, TMA operands); the rest in FP64',
 }
@@ -599,7 +606,7 @@ ENGINE_TOL = {'f64': 1e-8, 'f64_ozaki': 1e-8, 'tf32x3': 2e-4, 'tf32': 5e-3}
 
 
 def engine_row(prec, vt, ops, torch, dist, world, group, dev, X, y, theta, w, st, hinv, idx, S_cols64, N, D, n_loc, reps,
-               timed):
+               timed, note_key=None):
     """One full step through the public API with GLMObjective(precision=prec), max over ranks, plus the
     two contraction kernels timed alone and the sampled-column error against the FP64 DMMA result."""
     o32 = vt.objectives.GLMObjective(X, y, family='logistic', group=group, precision=prec)
@@ -622,7 +629,7 @@ def engine_row(prec, vt, ops, torch, dist, world, group, dev, X, y, theta, w, st
                          else '{:g} normwise'.format(ENGINE_TOL[prec])),
            'within_tolerance': bool(bar <= 1.0) if prec in ('f64', 'f64_ozaki') else bool(err_norm <= ENGINE_TOL[prec]),
            'ij_apply_ms': t_ap, 'ij_apply_fp64_equiv_tflops': 2.0 * D * D * n_loc / (t_ap * 1e-3) / 1e12,
-           'engine': ENGINE_NOTES[prec]}
+           'engine': ENGINE_NOTES[note_key or prec]}
     t_sy, _h = timed(lambda: ops.syrk_weighted(X, st['s'], precision=prec), reps)
     row.update({'syrk_ms': t_sy, 'syrk_fp64_equiv_tflops_algorithmic': float(D) * (D + 1) * n_loc / (t_sy * 1e-3) / 1e12})
     return row
